@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Sema retrieval hot path on B200.
+
+Metric (BASELINE.json): QPS of the exact top-10 cosine scan over 10M x 384 fp32
+unit-norm embeddings, with the achieved fraction of the HBM roofline.  A "step" is one
+single-query search over the whole corpus.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        # this repo's CUDA path
+  python bench.py --impl reference ...                       # CPU search path (oracle port)
+
+N > 1 is launched by torchrun (one process per GPU, NCCL): the fixed corpus is row-
+sharded over the N GPUs (strong scaling), every rank scans its shard, the per-shard
+top-k lists are all-gathered over NVLink and merged by kernel K4 on every rank.
+
+The reference (Rust + un-vendored LanceDB) cannot be built here, so the reference arm and
+the cpu_baseline leg time oracle/cpu_scan.c — the CPU restatement of the reference's
+search path — on the box's host cores ("kind": "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "qps_exact_top10_cosine_scan_10Mx384_fp32"
+L2_BYTES = 126e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000, help="total corpus rows")
+    ap.add_argument("--dim", type=int, default=384)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--queries", type=int, default=64, help="distinct query vectors cycled through")
+    ap.add_argument("--variant", type=int, default=-1, help="K2 kernel variant (tuning)")
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"{a.rows}x{a.dim} fp32 unit-norm synthetic embeddings, single-query exact top-{a.k} cosine scan"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device_index: int, period_s: float = 0.02):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period = period_s
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = device_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[device_index])
+                except ValueError:
+                    phys = device_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.nv = None
+            self.err = str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_scan_qps(a, steps, warmup):
+    """Times the oracle port (oracle/cpu_scan.c, all host threads) on a bounded sample:
+    the first `cpu_rows` rows of the same synthetic corpus.  Returns QPS scaled to the
+    full corpus (x sample_rows / rows: the scan is linear in rows) and a description."""
+    from oracle import c_oracle  # the ONLY use of oracle/ in bench.py: the CPU baseline
+    c_oracle.build()
+    n = min(a.cpu_rows, a.rows)
+    X = c_oracle.normalize(c_oracle.synth(1, 0, n, a.dim))
+    Q = c_oracle.normalize(c_oracle.synth(2, 0, a.queries, a.dim))
+    for i in range(warmup):
+        c_oracle.scan(X, Q[i % len(Q)], a.k)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        c_oracle.scan(X, Q[i % len(Q)], a.k)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    qps_sample = 1.0 / dt
+    scale = n / a.rows
+    return {
+        "value": qps_sample * scale, "unit": "queries/s", "cores": c_oracle.threads(), "kind": "port",
+        "sample": (f"oracle/cpu_scan.c (C port of the reference's CPU search path; the Rust reference "
+                   f"cannot be built here), {c_oracle.threads()} OpenMP threads, {steps} scans of the first "
+                   f"{n} rows x {a.dim} of the same corpus at {dt * 1e3:.2f} ms/scan "
+                   f"({n * a.dim * 4 / dt / 1e9:.1f} GB/s); QPS scaled by {n}/{a.rows} to the full corpus"),
+        "ms_per_scan_sample": dt * 1e3,
+    }
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(a.steps, 1), max(a.warmup, 0)
+    # bound the CPU work: the whole run must end within a few minutes
+    steps, warm = min(steps, 50), min(warm, 5)
+    base = cpu_scan_qps(a, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "queries/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": a.k,
+                   "note": "each step is one CPU scan of a bounded row sample, scaled linearly to the full corpus"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def make_queries(a, sema_b200, device):
+    """Unit-norm query vectors: synthetic rows (seed 2) normalised by kernel K1."""
+    from sema_b200.synth import synth_rows
+    raw = synth_rows(2, 0, a.queries, a.dim)
+    with sema_b200.GpuIndex(a.dim, a.queries, device=device) as qi:
+        qi.append(raw, normalize=True)
+        return qi.read_rows(0, a.queries)
+
+
+def run_ours(a):
+    import torch
+
+    import sema_b200
+    from sema_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus != world:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun (one process per GPU)")
+    if _lib.lib().sema_device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: sema_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- corpus: rows [lo, hi) of the fixed synthetic corpus live on this GPU
+    per = (a.rows + world - 1) // world
+    lo, hi = min(rank * per, a.rows), min((rank + 1) * per, a.rows)
+    idx = sema_b200.GpuIndex(a.dim, max(hi - lo, 1), device=local)
+    idx.set_row_base(lo)
+    idx.append_synthetic(seed=1, row0=lo, n=hi - lo, normalize=True)
+    if a.variant >= 0:
+        idx.set_scan_variant(a.variant)
+    Q = make_queries(a, sema_b200, local)
+    k = a.k
+
+    stream = torch.cuda.current_stream()
+    idx.set_stream(stream.cuda_stream)
+    Qd = torch.from_numpy(Q).to(dev)
+    qptr = [Qd[i].data_ptr() for i in range(a.queries)]
+    ids_d = torch.zeros(k, dtype=torch.int64, device=dev)
+    sc_d = torch.zeros(k, dtype=torch.float32, device=dev)
+    nf_d = torch.zeros(1, dtype=torch.int32, device=dev)
+    keys_local = torch.zeros(k, dtype=torch.int64, device=dev)
+    keys_all = torch.zeros(world * k, dtype=torch.int64, device=dev)
+
+    def step_device(i):
+        q = qptr[i % a.queries]
+        if world == 1:
+            idx.search_device(q, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+        else:
+            idx.search_keys_device(q, k, keys_local.data_ptr())
+            dist.all_gather_into_tensor(keys_all, keys_local)
+            idx.merge_device(keys_all.data_ptr(), world, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed region: inputs resident in HBM, CUDA events on the launching stream
+    for i in range(a.warmup):
+        step_device(i)
+    barrier()
+    l0 = idx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record(stream)
+        for i in range(a.steps):
+            step_device(i)
+        e1.record(stream)
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        launches = idx.launch_count - l0
+
+        # ---- end-to-end region: host query in, host results out, through the public call
+        ids_h = np.zeros(k, dtype=np.uint64)
+        sc_h = np.zeros(k, dtype=np.float32)
+        e2e_ms = None
+        if world == 1:
+            idx.set_stream(None)
+            for i in range(min(a.warmup, 5)):
+                idx.search_into(Q[i % a.queries], k, ids_h, sc_h)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(a.steps):
+                idx.search_into(Q[i % a.queries], k, ids_h, sc_h)
+            torch.cuda.synchronize()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
+        else:
+            from sema_b200.sharded import ShardedSearcher
+            sh = ShardedSearcher(idx, dist, k)
+            for i in range(min(a.warmup, 5)):
+                sh.search(Q[i % a.queries])
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(a.steps):
+                sh.search(Q[i % a.queries])
+            barrier()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    ms_step = dev_ms / a.steps
+    qps = 1e3 / ms_step
+    e2e_qps = a.steps / (e2e_ms / 1e3)
+
+    # ---- verification of the last device-side result against a fresh host-API search
+    verified = None
+    if not a.no_verify and world == 1:
+        i = (a.steps - 1) % a.queries
+        r_ids, r_sc = idx.search(Q[i], k)
+        verified = bool(np.array_equal(ids_d.cpu().numpy().astype(np.uint64), r_ids))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_src = "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        pk_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    shard_rows = hi - lo
+    bytes_per_launch = shard_rows * a.dim * 4          # algorithmic bytes: the shard read once
+    achieved = bytes_per_launch / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": workload_name(a), "rows": a.rows, "dim": a.dim, "k": k,
+            "rows_per_gpu": shard_rows, "query_pool": a.queries,
+            "l2_flush": f"none needed: each step streams {bytes_per_launch / 1e9:.2f} GB per GPU, "
+                        f"{bytes_per_launch / L2_BYTES:.0f}x the 126 MB L2",
+            "parallelism": "single GPU" if world == 1 else f"corpus row-sharded over {world} GPUs, NCCL all-gather of per-shard top-k + K4 merge",
+            "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
+        },
+        "roofline": {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": pk_src,
+            "kernel": "scan_topk_kernel (K2)",
+            "note": "achieved = rows_per_gpu*dim*4 bytes / device time per step (one K2 launch per step"
+                    + ("" if world == 1 else " plus the all-gather and the K4 merge") + ")",
+        },
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": ((a.dim + 3) // 4) * 16,
+                "d2h_bytes_per_step": 8 + 12 * k, "ms_per_step": e2e_ms / a.steps,
+                "path": "sema_index_search (C ABI) with host buffers: query H2D, K2, result D2H, stream sync"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "verified_against_host_api": verified,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_scan_qps(a, a.cpu_steps, 2)
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

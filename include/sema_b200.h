@@ -1,0 +1,147 @@
+/*
+ * sema_b200.h — C ABI of the B200-native exact vector-search path for Sema.
+ *
+ * This is the drop-in boundary for ONE path of akshitsinha/sema: the flat exact
+ * nearest-neighbour scan with top-k over the chunk-embedding index.  Every entry
+ * point names the reference interface (file:line under the reference tree) it
+ * replaces.  Plain pointers and sizes only; no C++/torch types; nothing throws or
+ * aborts across this boundary.  All functions return SEMA_OK (0) or a negative
+ * SEMA_ERR_* code; sema_last_error() returns a thread-local description.
+ *
+ * Threading: a handle may be used from different OS threads (the reference's tokio
+ * runtime moves `&mut self` calls between workers, src/storage/mod.rs:112) but by
+ * at most one thread at a time; every entry point re-binds the CUDA device.
+ * There is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef SEMA_B200_H
+#define SEMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEMA_OK 0
+#define SEMA_ERR_INVALID (-1)     /* bad argument                               */
+#define SEMA_ERR_CUDA (-2)        /* CUDA runtime/driver error                  */
+#define SEMA_ERR_CAPACITY (-3)    /* append would exceed capacity_rows          */
+#define SEMA_ERR_NOMEM (-4)       /* host or device allocation failed           */
+#define SEMA_ERR_UNSUPPORTED (-5) /* shape outside what the kernels cover       */
+
+/* Ranking metric.  The reference never sets distance_type() on its query
+ * (src/storage/lance_indexer.rs:121-126), i.e. LanceDB's default squared L2,
+ * ascending; on the unit-norm rows the embedder produces
+ * (src/semantic/embeddings.rs:83-88) that order equals descending cosine. */
+#define SEMA_METRIC_COSINE 0 /* score = q.x (cosine on unit rows), best = largest        */
+#define SEMA_METRIC_L2 1     /* score = sum (q-x)^2 = LanceDB `_distance`, best = smallest */
+
+#define SEMA_MAX_K 1024u   /* largest `limit`; k <= 128 is one fused pass, larger k = ceil(k/128) passes */
+#define SEMA_MAX_DIM 8192u /* dim 384 / 768 have unrolled kernels; others use the generic kernel */
+
+typedef struct sema_index sema_index;
+
+/* ---- lifecycle -----------------------------------------------------------
+ * Replaces LanceIndexer::new (src/storage/lance_indexer.rs:19-28) +
+ * create_table("chunks") (:97-101).  The handle owns the row-major, 16-byte
+ * aligned fp32 matrix in HBM (capacity_rows x round_up(dim,4)), its streams and
+ * staging buffers.  metric is SEMA_METRIC_*. */
+int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metric,
+                      sema_index **out);
+int sema_index_destroy(sema_index *idx);
+
+/* ---- ingest (kernel K1) --------------------------------------------------
+ * Replaces the vector half of LanceIndexer::index_chunks
+ * (src/storage/lance_indexer.rs:30-105): `rows` is the contiguous n x dim f32
+ * values buffer of the FixedSizeList<Float32,dim> column (:75-76); `valid` is its
+ * validity (one byte per row, 0 = null vector = failed embedding, :66-70) or NULL
+ * for "all valid".  normalize != 0 applies the mean_pool tail
+ * (src/semantic/embeddings.rs:83-88) on the device.  Null rows and rows holding a
+ * non-finite value are never returned by a search.  On return the rows are
+ * visible to every later search (table.add(..).await, :92-95); *first_row (may be
+ * NULL) receives the local row index of rows[0]. */
+int sema_index_append(sema_index *idx, const float *rows, uint64_t n, const uint8_t *valid,
+                      int normalize, uint64_t *first_row);
+/* Same, but returns once the copy + K1 are enqueued on the ingest stream; `rows`
+ * and `valid` must stay untouched until sema_index_flush() (use pinned memory from
+ * sema_host_alloc for a truly asynchronous copy).  Rows become visible to searches
+ * that start after their ingest has completed on the device (snapshot semantics). */
+int sema_index_append_async(sema_index *idx, const float *rows, uint64_t n,
+                            const uint8_t *valid, int normalize, uint64_t *first_row);
+int sema_index_flush(sema_index *idx);
+/* rows already resident on this device (n x dim, dense). */
+int sema_index_append_device(sema_index *idx, const float *rows_dev, uint64_t n,
+                             const uint8_t *valid_dev, int normalize, uint64_t *first_row);
+/* Benchmark/test corpus generated on the device: value(seed,row,col) of SURVEY.md
+ * §8(d) (bit-identical to oracle/cpu_scan.c:sema_oracle_synth) for rows
+ * [synth_row0, synth_row0+n), then K1. */
+int sema_index_append_synthetic(sema_index *idx, uint64_t seed, uint64_t synth_row0, uint64_t n,
+                                int normalize, uint64_t *first_row);
+
+/* Replaces remove_file_chunks' `table.delete(predicate)`
+ * (src/storage/lance_indexer.rs:234-250): the listed local rows stop matching. */
+int sema_index_tombstone(sema_index *idx, const uint64_t *rows, uint64_t n);
+
+/* ---- search (kernel K2; K3 for batches) -----------------------------------
+ * Replaces table.query().nearest_to(q)?.limit(k).execute()
+ * (src/storage/lance_indexer.rs:121-126).  q: dim floats (unit-norm for cosine).
+ * Out (caller-allocated, k entries): row_ids = row_base + local row, best first;
+ * scores = cosine (descending) or squared-L2 `_distance` (ascending).  Exact ties
+ * rank the lower row id first.  *n_found = min(k, visible valid rows); an empty
+ * index is SEMA_OK with *n_found = 0 (:108-111). */
+int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row_ids,
+                      float *scores, uint32_t *n_found);
+/* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq]. */
+int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32_t k,
+                            uint64_t *row_ids, float *scores, uint32_t *n_found);
+
+/* ---- device-resident variants (no host copies, no synchronisation) --------
+ * Used for kernel-only timing and by the sharded path.  q_dev: dim floats on the
+ * device.  keys_dev: k packed 64-bit ranking keys, best first, 0 = empty slot:
+ *   key = ordered_u32(rank value) << 32 | (0xFFFFFFFF - global_row_id)
+ * so that a plain unsigned compare orders by score then by lower row id.  Work is
+ * enqueued on the index's query stream (see sema_index_set_stream). */
+int sema_index_search_keys_device(sema_index *idx, const float *q_dev, uint32_t k,
+                                  uint64_t *keys_dev);
+/* Same search with the decoded result left on the device: ids_dev/scores_dev hold k
+ * entries, n_found_dev one uint32 (for callers whose embedder already runs on the GPU). */
+int sema_index_search_device(sema_index *idx, const float *q_dev, uint32_t k, uint64_t *ids_dev,
+                             float *scores_dev, uint32_t *n_found_dev);
+/* Kernel K4: merge n_lists ranked key lists of k entries each (e.g. the allgathered
+ * per-shard results) into the global top-k and decode it.  All pointers are device
+ * pointers; ids_dev/scores_dev hold k entries, n_found_dev one uint32. */
+int sema_topk_merge_device(sema_index *idx, const uint64_t *keys_dev, uint32_t n_lists,
+                           uint32_t k, uint64_t *ids_dev, float *scores_dev,
+                           uint32_t *n_found_dev);
+
+/* ---- properties ------------------------------------------------------------ */
+int sema_index_set_row_base(sema_index *idx, uint64_t row_base); /* shard offset of row 0   */
+/* external != 0: run searches on the caller's cudaStream_t `cuda_stream` (0 = the CUDA
+ * default stream); external == 0: back to the handle's own non-blocking query stream. */
+int sema_index_set_stream(sema_index *idx, void *cuda_stream, int external);
+uint64_t sema_index_size(const sema_index *idx);     /* rows appended (visible + in flight) */
+uint64_t sema_index_visible(sema_index *idx);        /* rows a search starting now would scan */
+uint64_t sema_index_capacity(const sema_index *idx);
+uint32_t sema_index_dim(const sema_index *idx);
+int sema_index_device(const sema_index *idx);
+/* snapshot (visible rows) the most recent search on this handle scanned */
+uint64_t sema_index_last_snapshot(const sema_index *idx);
+/* copy stored (normalised) rows back to the host: out = n x dim floats */
+int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float *out);
+/* tuning: variant < 0 = default.  Returns the variant now active. */
+int sema_index_set_scan_variant(sema_index *idx, int variant);
+/* number of kernels this handle has launched so far */
+uint64_t sema_index_launch_count(const sema_index *idx);
+
+/* ---- misc -------------------------------------------------------------------- */
+int sema_host_alloc(void **out, size_t bytes); /* pinned host memory */
+int sema_host_free(void *p);
+int sema_device_count(void);
+const char *sema_last_error(void);
+const char *sema_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMA_B200_H */

@@ -1,0 +1,224 @@
+// k2_scan.cuh — kernel K2: single-query exact scan with fused top-k.
+//
+// Replaces LanceDB's flat KNN behind table.query().nearest_to(q)?.limit(k).execute()
+// (reference: src/storage/lance_indexer.rs:121-126).  HBM-bandwidth bound: the
+// N x ld fp32 matrix is streamed exactly once (algorithmic bytes N*d*4), the query
+// lives in registers, and selection never leaves the SM until the per-block lists
+// are merged by the last block to finish (single launch, graph-replayable).
+//
+// Work split: a warp owns batches of R consecutive rows.  A row is NV*32 float4
+// (NV = 3 for d=384, 6 for d=768); lane l loads float4 l, l+32, ... of each row,
+// i.e. every warp-level LDG.128 covers 512 contiguous bytes.  The R partial sums
+// per lane are reduced with a transposed butterfly (R-1 + log2(32/R) shuffles per R
+// rows instead of 5R), after which lane L holds the finished score of one row and
+// offers it to the warp's top-k list.
+#pragma once
+#include "common.cuh"
+
+namespace sema {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+
+struct ScanParams {
+    const float4 *X;        // row-major, row stride ld4 float4
+    const float *q;         // ld floats, zero padded, device
+    uint64_t *partials;     // gridDim.x * 32*M keys
+    unsigned int *ticket;   // self-resetting arrival counter
+    const uint64_t *bound;  // nullable: only keys < *bound compete (multi-pass k > 128)
+    uint64_t *out_keys;     // k keys, best first, 0 = empty
+    // optional fused decode (single pass), all nullable together
+    uint64_t *res_ids;      // k global row ids
+    float *res_scores;      // k scores (cosine) or distances (L2)
+    uint32_t *res_nfound;
+    uint32_t n;             // rows to scan (snapshot)
+    uint32_t ld4;           // row stride in float4
+    uint32_t k;
+    uint32_t row_base;      // global id of local row 0
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <int METRIC>
+__device__ __forceinline__ float accum4(float a, const float4 x, const float4 q)
+{
+    if (METRIC == METRIC_L2) {
+        float t;
+        t = q.x - x.x; a = fmaf(t, t, a);
+        t = q.y - x.y; a = fmaf(t, t, a);
+        t = q.z - x.z; a = fmaf(t, t, a);
+        t = q.w - x.w; a = fmaf(t, t, a);
+    } else {
+        a = fmaf(x.x, q.x, a);
+        a = fmaf(x.y, q.y, a);
+        a = fmaf(x.z, q.z, a);
+        a = fmaf(x.w, q.w, a);
+    }
+    return a;
+}
+
+// Transposed butterfly: in: acc[r] = this lane's partial of row r; out: the full sum
+// of row rows_of_lane<R>(lane), replicated over the 32/R lanes that share it.
+template <int R>
+__device__ __forceinline__ float reduce_rows(float (&acc)[R], int lane)
+{
+#pragma unroll
+    for (int half = R / 2, d = 16; half >= 1; half >>= 1, d >>= 1) {
+        const bool up = (lane & d) != 0;
+#pragma unroll
+        for (int r = 0; r < half; ++r) {
+            const float keep = up ? acc[r + half] : acc[r];
+            const float send = up ? acc[r] : acc[r + half];
+            acc[r] = keep + __shfl_xor_sync(FULL, send, d);
+        }
+    }
+#pragma unroll
+    for (int d = 16 / R; d >= 1; d >>= 1) acc[0] += __shfl_xor_sync(FULL, acc[0], d);
+    return acc[0];
+}
+
+template <int R>
+__device__ __forceinline__ int row_of_lane(int lane)
+{
+    int r = 0;
+#pragma unroll
+    for (int half = R / 2, d = 16; half >= 1; half >>= 1, d >>= 1)
+        if (lane & d) r += half;
+    return r;
+}
+
+// Decode one key into the boundary's (row id, score) pair.
+template <int METRIC>
+__device__ __forceinline__ void decode_key(uint64_t key, uint64_t &id, float &score)
+{
+    const float rank = key_rank(key);
+    id = key ? (uint64_t)key_gid(key) : 0ull;
+    score = key ? (METRIC == METRIC_L2 ? -rank + 0.0f : rank) : 0.0f;
+}
+
+// Write the sorted key list held by warp 0 (and, optionally, its decoded form).
+template <int M, int METRIC>
+__device__ __forceinline__ void emit_results(const WarpTopK<M> &top, int k, uint64_t *out_keys,
+                                             uint64_t *res_ids, float *res_scores,
+                                             uint32_t *res_nfound, int lane)
+{
+    int found = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        const int e = j * 32 + lane;
+        const bool in = e < k;
+        if (in && out_keys) out_keys[e] = top.v[j];
+        found += __popc(__ballot_sync(FULL, in && top.v[j] != 0));
+        if (res_ids && in) decode_key<METRIC>(top.v[j], res_ids[e], res_scores[e]);
+    }
+    if (res_nfound && lane == 0) *res_nfound = (uint32_t)found;
+}
+
+// NV > 0: row is exactly NV*32 float4 (unrolled, query in registers).
+// NV == 0: generic row length (query in shared memory, lane-strided loop).
+template <int NV, int R, int M, int METRIC>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_topk_kernel(const ScanParams p)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ uint64_t sm_keys[SCAN_WARPS * 32 * M];
+    __shared__ bool is_last;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t n = p.n;
+    const uint32_t ld4 = p.ld4;
+    const int k = (int)p.k;
+    const uint64_t bound = p.bound ? *p.bound : ~0ull;
+
+    constexpr int NVR = NV > 0 ? NV : 1;
+    float4 qv[NVR];
+    float4 *qs = reinterpret_cast<float4 *>(dyn_smem);
+    if (NV > 0) {
+#pragma unroll
+        for (int v = 0; v < NVR; ++v) qv[v] = reinterpret_cast<const float4 *>(p.q)[v * 32 + lane];
+    } else {
+        for (uint32_t i = threadIdx.x; i < ld4; i += SCAN_THREADS)
+            qs[i] = reinterpret_cast<const float4 *>(p.q)[i];
+        __syncthreads();
+    }
+
+    WarpTopK<M> top;
+    top.init();
+
+    const uint32_t nb = (n + R - 1) / R;
+    const uint32_t gw = blockIdx.x * SCAN_WARPS + warp;
+    const uint32_t nw = gridDim.x * SCAN_WARPS;
+    const int my_r = row_of_lane<R>(lane);
+    const bool rep = (lane & (32 / R - 1)) == 0;
+
+    for (uint32_t b = gw; b < nb; b += nw) {
+        const uint32_t row0 = b * R;
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+
+        if (NV > 0) {
+            float4 x[R][NVR];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t row = min(row0 + r, n - 1);
+                const float4 *xp = p.X + (size_t)row * ld4 + lane;
+#pragma unroll
+                for (int v = 0; v < NVR; ++v) x[r][v] = ldg_stream(xp + v * 32);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int v = 0; v < NVR; ++v) acc[r] = accum4<METRIC>(acc[r], x[r][v], qv[v]);
+        } else {
+            for (uint32_t i = lane; i < ld4; i += 32) {
+                const float4 qq = qs[i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t row = min(row0 + r, n - 1);
+                    acc[r] = accum4<METRIC>(acc[r], ldg_stream(p.X + (size_t)row * ld4 + i), qq);
+                }
+            }
+        }
+
+        const float s = reduce_rows<R>(acc, lane);
+        const uint32_t row = row0 + my_r;
+        const float rank = (METRIC == METRIC_L2) ? -s : s;
+        const uint64_t key = make_key(rank, p.row_base + row);
+        top.offer(key, rep && row < n && s == s && key < bound, lane, k);
+    }
+
+    // ---- block merge, then the last block to arrive merges all partial lists ----
+    block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
+    if (warp == 0) top.store(p.partials + (size_t)blockIdx.x * 32 * M, lane);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    top.init();
+    const int chunks = (k + 31) >> 5;
+    const int total = (int)gridDim.x * chunks;
+    for (int i = warp; i < total; i += SCAN_WARPS) {
+        const int bb = i / chunks, j = i - bb * chunks;
+        const uint64_t key = __ldcg(p.partials + (size_t)bb * 32 * M + j * 32 + lane);
+        top.offer(key, key != 0, lane, k);
+    }
+    block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
+    if (warp == 0) {
+        emit_results<M, METRIC>(top, k, p.out_keys, p.res_ids, p.res_scores, p.res_nfound, lane);
+        if (lane == 0) *p.ticket = 0;
+    }
+}
+
+}  // namespace sema

@@ -1,0 +1,676 @@
+// sema_api.cu — host side of the C ABI declared in include/sema_b200.h.
+//
+// Owns the HBM layout (row-major fp32, row stride ld = round_up(dim,4) floats, base
+// 256-byte aligned by cudaMalloc, so every row is 16-byte aligned), the streams and
+// the small staging buffers; dispatches to K1 (ingest), K2 (scan + top-k) and K4
+// (merge).  No CPU fallback exists: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <deque>
+#include <mutex>
+#include <new>
+
+#include "../../include/sema_b200.h"
+#include "k1_ingest.cuh"
+#include "k2_scan.cuh"
+#include "k4_merge.cuh"
+
+using namespace sema;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(SEMA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+struct Pending {
+    cudaEvent_t ev;
+    uint64_t rows_after;
+};
+
+constexpr int K_PASS = 128;  // keys one fused pass can select (WarpTopK<4>)
+constexpr int MAX_BLOCKS_PER_SM = 8;
+
+}  // namespace
+
+struct sema_index {
+    int device = 0;
+    uint32_t dim = 0, ld = 0;
+    uint64_t capacity = 0;
+    int metric = 0;
+    int num_sms = 0;
+    float *X = nullptr;
+    uint8_t *valid = nullptr;
+    uint64_t n_rows = 0;     // appended (enqueued)
+    uint64_t n_visible = 0;  // ingest completed on the device
+    uint64_t last_snapshot = 0;
+    uint32_t row_base = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, ingest_stream = nullptr;
+    float *q_dev = nullptr;           // ld floats
+    float *q_pin = nullptr;           // pinned, ld floats
+    uint64_t *partials = nullptr;     // num_sms * MAX_BLOCKS_PER_SM * 128 keys
+    unsigned int *ticket = nullptr;
+    uint64_t *keys_dev = nullptr;     // SEMA_MAX_K keys (multi-pass scratch)
+    unsigned char *res_dev = nullptr; // [n_found u32, pad][ids u64 K][scores f32 K]
+    unsigned char *res_pin = nullptr;
+    // batch buffers, grown on demand
+    float *Q_dev = nullptr;
+    uint64_t *bids_dev = nullptr;
+    float *bsc_dev = nullptr;
+    uint32_t *bnf_dev = nullptr;
+    size_t batch_cap_q = 0, batch_cap_res = 0;
+    uint64_t *tomb_dev = nullptr;
+    size_t tomb_cap = 0;
+    std::deque<Pending> pending;
+    int variant = 0;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int poll_ingest(sema_index *s, bool wait)
+{
+    while (!s->pending.empty()) {
+        Pending &p = s->pending.front();
+        cudaError_t e = wait ? cudaEventSynchronize(p.ev) : cudaEventQuery(p.ev);
+        if (e == cudaErrorNotReady) break;
+        if (e != cudaSuccess) return fail(SEMA_ERR_CUDA, "ingest event: %s", cudaGetErrorString(e));
+        s->n_visible = p.rows_after;
+        cudaEventDestroy(p.ev);
+        s->pending.pop_front();
+    }
+    return SEMA_OK;
+}
+
+// ---- K2 dispatch ---------------------------------------------------------------
+struct ScanArgs {
+    const float *q_dev;
+    uint32_t n, k;
+    const uint64_t *bound;
+    uint64_t *out_keys;
+    uint64_t *res_ids;
+    float *res_scores;
+    uint32_t *res_nfound;
+};
+
+template <int NV, int R, int M, int METRIC>
+int run_scan(sema_index *s, const ScanArgs &a)
+{
+    auto kern = scan_topk_kernel<NV, R, M, METRIC>;
+    static int occ[64] = {0};  // per device
+    const size_t dyn = NV > 0 ? 0 : (size_t)s->ld * sizeof(float);
+    int &o = occ[s->device & 63];
+    if (o == 0 || NV == 0) {
+        int t = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t, kern, SCAN_THREADS, dyn));
+        if (t < 1) return fail(SEMA_ERR_UNSUPPORTED, "scan kernel does not fit on an SM");
+        o = t > MAX_BLOCKS_PER_SM ? MAX_BLOCKS_PER_SM : t;
+    }
+    const uint32_t nb = (a.n + R - 1) / R;
+    uint32_t grid = (uint32_t)(s->num_sms * o);
+    const uint32_t need = (nb + SCAN_WARPS - 1) / SCAN_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    ScanParams p;
+    p.X = reinterpret_cast<const float4 *>(s->X);
+    p.q = a.q_dev;
+    p.partials = s->partials;
+    p.ticket = s->ticket;
+    p.bound = a.bound;
+    p.out_keys = a.out_keys;
+    p.res_ids = a.res_ids;
+    p.res_scores = a.res_scores;
+    p.res_nfound = a.res_nfound;
+    p.n = a.n;
+    p.ld4 = s->ld / 4;
+    p.k = a.k;
+    p.row_base = s->row_base;
+    kern<<<grid, SCAN_THREADS, dyn, s->stream>>>(p);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+template <int NV, int R, int METRIC>
+int scan_m(sema_index *s, const ScanArgs &a)
+{
+    if (a.k <= 32) return run_scan<NV, R, 1, METRIC>(s, a);
+    if (a.k <= 64) return run_scan<NV, R, 2, METRIC>(s, a);
+    return run_scan<NV, R, 4, METRIC>(s, a);
+}
+
+template <int METRIC>
+int scan_shape(sema_index *s, const ScanArgs &a)
+{
+    const uint32_t ld4 = s->ld / 4;
+    if (ld4 == 96) {
+        switch (s->variant) {
+            case 1: return scan_m<3, 8, METRIC>(s, a);
+            case 2: return scan_m<3, 2, METRIC>(s, a);
+            default: return scan_m<3, 4, METRIC>(s, a);
+        }
+    }
+    if (ld4 == 192) {
+        switch (s->variant) {
+            case 2: return scan_m<6, 2, METRIC>(s, a);
+            default: return scan_m<6, 4, METRIC>(s, a);
+        }
+    }
+    return scan_m<0, 4, METRIC>(s, a);
+}
+
+// one fused pass (k <= K_PASS)
+int scan_pass(sema_index *s, const ScanArgs &a)
+{
+    return s->metric == SEMA_METRIC_L2 ? scan_shape<METRIC_L2>(s, a) : scan_shape<METRIC_COSINE>(s, a);
+}
+
+template <int METRIC>
+int merge_pass_m(sema_index *s, const uint64_t *keys, uint32_t total, uint32_t k,
+                 const uint64_t *bound, uint64_t *out_keys, uint64_t *ids, float *sc, uint32_t *nf)
+{
+    if (k <= 32)
+        merge_topk_kernel<1, METRIC><<<1, MERGE_THREADS, 0, s->stream>>>(keys, total, (int)k, bound, out_keys, ids, sc, nf);
+    else if (k <= 64)
+        merge_topk_kernel<2, METRIC><<<1, MERGE_THREADS, 0, s->stream>>>(keys, total, (int)k, bound, out_keys, ids, sc, nf);
+    else
+        merge_topk_kernel<4, METRIC><<<1, MERGE_THREADS, 0, s->stream>>>(keys, total, (int)k, bound, out_keys, ids, sc, nf);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+int decode(sema_index *s, const uint64_t *keys, uint32_t k, uint64_t *ids, float *sc, uint32_t *nf)
+{
+    if (s->metric == SEMA_METRIC_L2)
+        decode_kernel<METRIC_L2><<<1, 256, 0, s->stream>>>(keys, (int)k, ids, sc, nf);
+    else
+        decode_kernel<METRIC_COSINE><<<1, 256, 0, s->stream>>>(keys, (int)k, ids, sc, nf);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+// Full selection of the best k (any k <= SEMA_MAX_K) for one query that is already on
+// the device.  Exactly one of {out_keys} / {res_*} may be null.
+int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys,
+               uint64_t *res_ids, float *res_scores, uint32_t *res_nfound)
+{
+    if (k <= K_PASS) {
+        ScanArgs a{q_dev, n, k, nullptr, out_keys ? out_keys : s->keys_dev, res_ids, res_scores, res_nfound};
+        return scan_pass(s, a);
+    }
+    uint64_t *keys = out_keys ? out_keys : s->keys_dev;
+    for (uint32_t done = 0; done < k; done += K_PASS) {
+        const uint32_t kp = (k - done) < (uint32_t)K_PASS ? (k - done) : (uint32_t)K_PASS;
+        ScanArgs a{q_dev, n, kp, done ? keys + done - 1 : nullptr, keys + done, nullptr, nullptr, nullptr};
+        int rc = scan_pass(s, a);
+        if (rc) return rc;
+    }
+    if (res_ids) return decode(s, keys, k, res_ids, res_scores, res_nfound);
+    return SEMA_OK;
+}
+
+int ensure(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return SEMA_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CK(cudaMalloc(p, need));
+    *cap = need;
+    return SEMA_OK;
+}
+
+int launch_ingest(sema_index *s, const float *src, uint64_t src_ld, uint64_t first, uint64_t n,
+                  const uint8_t *valid_in, int normalize, bool vec4)
+{
+    float *dst = s->X + first * s->ld;
+    uint64_t warps_needed = n;
+    uint64_t blocks = (warps_needed * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+    const uint64_t maxb = (uint64_t)s->num_sms * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    if (vec4)
+        ingest_kernel<true><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
+            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize);
+    else
+        ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
+            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+int publish(sema_index *s, uint64_t n)
+{
+    s->n_rows += n;
+    Pending p;
+    CK(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(p.ev, s->ingest_stream));
+    p.rows_after = s->n_rows;
+    s->pending.push_back(p);
+    return SEMA_OK;
+}
+
+int check_append(sema_index *s, uint64_t n)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (s->n_rows + n > s->capacity)
+        return fail(SEMA_ERR_CAPACITY, "append of %llu rows exceeds capacity %llu (size %llu)",
+                    (unsigned long long)n, (unsigned long long)s->capacity, (unsigned long long)s->n_rows);
+    if ((uint64_t)s->row_base + s->n_rows + n > 0xfffffffeull)
+        return fail(SEMA_ERR_CAPACITY, "global row ids must stay below 2^32-1");
+    return SEMA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sema_last_error(void) { return g_err; }
+const char *sema_version(void) { return "sema_b200 0.1 (sm_100a)"; }
+
+int sema_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int sema_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return fail(SEMA_ERR_INVALID, "null out");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return SEMA_OK;
+}
+
+int sema_host_free(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return SEMA_OK;
+}
+
+int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metric, sema_index **out)
+{
+    if (!out) return fail(SEMA_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (dim == 0 || dim > SEMA_MAX_DIM) return fail(SEMA_ERR_INVALID, "dim %u outside [1, %u]", dim, SEMA_MAX_DIM);
+    if (metric != SEMA_METRIC_COSINE && metric != SEMA_METRIC_L2) return fail(SEMA_ERR_INVALID, "unknown metric %d", metric);
+    if (capacity_rows > 0xfffffffeull) return fail(SEMA_ERR_INVALID, "capacity_rows must be < 2^32-1");
+    int ndev = sema_device_count();
+    if (ndev == 0) return fail(SEMA_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(SEMA_ERR_INVALID, "device %d outside [0, %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    sema_index *s = new (std::nothrow) sema_index();
+    if (!s) return fail(SEMA_ERR_NOMEM, "host allocation failed");
+    s->device = device;
+    s->dim = dim;
+    s->ld = (dim + 3u) & ~3u;
+    s->capacity = capacity_rows;
+    s->metric = metric;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete s; return fail(SEMA_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    s->num_sms = prop.multiProcessorCount;
+    const size_t xbytes = (size_t)(capacity_rows ? capacity_rows : 1) * s->ld * sizeof(float);
+    const size_t res_bytes = 8 + (size_t)SEMA_MAX_K * 12;
+#define CKD(call)                                                                           \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            int code_ = e_ == cudaErrorMemoryAllocation ? SEMA_ERR_NOMEM : SEMA_ERR_CUDA;   \
+            fail(code_, "%s failed: %s", #call, cudaGetErrorString(e_));                    \
+            cudaGetLastError();                                                             \
+            sema_index_destroy(s);                                                          \
+            return code_;                                                                   \
+        }                                                                                   \
+    } while (0)
+    CKD(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    CKD(cudaStreamCreateWithFlags(&s->ingest_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    CKD(cudaMalloc(&s->X, xbytes));
+    CKD(cudaMalloc(&s->valid, capacity_rows ? capacity_rows : 1));
+    CKD(cudaMalloc(&s->q_dev, s->ld * sizeof(float)));
+    CKD(cudaMemset(s->q_dev, 0, s->ld * sizeof(float)));
+    CKD(cudaHostAlloc(&s->q_pin, s->ld * sizeof(float), cudaHostAllocPortable));
+    memset(s->q_pin, 0, s->ld * sizeof(float));
+    CKD(cudaMalloc(&s->partials, (size_t)s->num_sms * MAX_BLOCKS_PER_SM * K_PASS * sizeof(uint64_t)));
+    CKD(cudaMalloc(&s->ticket, sizeof(unsigned int)));
+    CKD(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
+    CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
+    CKD(cudaMalloc(&s->res_dev, res_bytes));
+    CKD(cudaHostAlloc(&s->res_pin, res_bytes, cudaHostAllocPortable));
+    CKD(cudaDeviceSynchronize());
+#undef CKD
+    *out = s;
+    return SEMA_OK;
+}
+
+int sema_index_destroy(sema_index *s)
+{
+    if (!s) return SEMA_OK;
+    cudaSetDevice(s->device);
+    if (s->own_stream) cudaStreamSynchronize(s->own_stream);
+    if (s->ingest_stream) cudaStreamSynchronize(s->ingest_stream);
+    for (auto &p : s->pending) cudaEventDestroy(p.ev);
+    cudaFree(s->X); cudaFree(s->valid); cudaFree(s->q_dev); cudaFreeHost(s->q_pin);
+    cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->keys_dev); cudaFree(s->res_dev);
+    cudaFreeHost(s->res_pin); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
+    cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->ingest_stream) cudaStreamDestroy(s->ingest_stream);
+    cudaGetLastError();
+    delete s;
+    return SEMA_OK;
+}
+
+int sema_index_append_async(sema_index *s, const float *rows, uint64_t n, const uint8_t *valid,
+                            int normalize, uint64_t *first_row)
+{
+    int rc = check_append(s, n);
+    if (rc) return rc;
+    if (n && !rows) return fail(SEMA_ERR_INVALID, "null rows");
+    CK(cudaSetDevice(s->device));
+    const uint64_t first = s->n_rows;
+    if (first_row) *first_row = first;
+    if (n == 0) return SEMA_OK;
+    float *dst = s->X + first * s->ld;
+    // host rows land directly in their final place; K1 then normalises in place
+    if (s->ld == s->dim)
+        CK(cudaMemcpyAsync(dst, rows, n * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->ingest_stream));
+    else
+        CK(cudaMemcpy2DAsync(dst, s->ld * sizeof(float), rows, s->dim * sizeof(float),
+                             s->dim * sizeof(float), n, cudaMemcpyHostToDevice, s->ingest_stream));
+    const uint8_t *vin = nullptr;
+    if (valid) {
+        CK(cudaMemcpyAsync(s->valid + first, valid, n, cudaMemcpyHostToDevice, s->ingest_stream));
+        vin = s->valid + first;
+    }
+    rc = launch_ingest(s, dst, s->ld, first, n, vin, normalize, s->ld == s->dim);
+    if (rc) return rc;
+    return publish(s, n);
+}
+
+int sema_index_flush(sema_index *s)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->ingest_stream));
+    return poll_ingest(s, true);
+}
+
+int sema_index_append(sema_index *s, const float *rows, uint64_t n, const uint8_t *valid,
+                      int normalize, uint64_t *first_row)
+{
+    int rc = sema_index_append_async(s, rows, n, valid, normalize, first_row);
+    if (rc) return rc;
+    return sema_index_flush(s);
+}
+
+int sema_index_append_device(sema_index *s, const float *rows_dev, uint64_t n,
+                             const uint8_t *valid_dev, int normalize, uint64_t *first_row)
+{
+    int rc = check_append(s, n);
+    if (rc) return rc;
+    if (n && !rows_dev) return fail(SEMA_ERR_INVALID, "null rows");
+    CK(cudaSetDevice(s->device));
+    const uint64_t first = s->n_rows;
+    if (first_row) *first_row = first;
+    if (n == 0) return SEMA_OK;
+    const bool vec4 = s->ld == s->dim && (reinterpret_cast<uintptr_t>(rows_dev) & 15) == 0;
+    rc = launch_ingest(s, rows_dev, s->dim, first, n, valid_dev, normalize, vec4);
+    if (rc) return rc;
+    rc = publish(s, n);
+    if (rc) return rc;
+    return sema_index_flush(s);
+}
+
+int sema_index_append_synthetic(sema_index *s, uint64_t seed, uint64_t synth_row0, uint64_t n,
+                                int normalize, uint64_t *first_row)
+{
+    int rc = check_append(s, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    const uint64_t first = s->n_rows;
+    if (first_row) *first_row = first;
+    if (n == 0) return SEMA_OK;
+    float *dst = s->X + first * s->ld;
+    synth_kernel<<<s->num_sms * 16, INGEST_THREADS, 0, s->ingest_stream>>>(dst, s->ld, s->dim, seed, synth_row0, n);
+    CK(cudaGetLastError());
+    s->launches++;
+    rc = launch_ingest(s, dst, s->ld, first, n, nullptr, normalize, s->ld == s->dim);
+    if (rc) return rc;
+    rc = publish(s, n);
+    if (rc) return rc;
+    return sema_index_flush(s);
+}
+
+int sema_index_tombstone(sema_index *s, const uint64_t *rows, uint64_t n)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (n && !rows) return fail(SEMA_ERR_INVALID, "null rows");
+    if (n == 0) return SEMA_OK;
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; ++i)
+        if (rows[i] >= s->n_rows)
+            return fail(SEMA_ERR_INVALID, "tombstone row %llu >= size %llu", (unsigned long long)rows[i], (unsigned long long)s->n_rows);
+    rc = ensure(reinterpret_cast<void **>(&s->tomb_dev), &s->tomb_cap, n * sizeof(uint64_t));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s->tomb_dev, rows, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    uint64_t blocks = (n * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+    if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
+    tombstone_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, s->tomb_dev, n, s->n_rows, s->valid);
+    CK(cudaGetLastError());
+    s->launches++;
+    CK(cudaStreamSynchronize(s->stream));
+    return SEMA_OK;
+}
+
+int sema_index_search(sema_index *s, const float *q, uint32_t k, uint64_t *row_ids, float *scores,
+                      uint32_t *n_found)
+{
+    if (!s || !q || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u > SEMA_MAX_K %u", k, SEMA_MAX_K);
+    if (k && (!row_ids || !scores)) return fail(SEMA_ERR_INVALID, "null output");
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    *n_found = 0;
+    if (k == 0 || n == 0) return SEMA_OK;
+    memcpy(s->q_pin, q, s->dim * sizeof(float));
+    CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
+    float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
+    rc = scan_query(s, s->q_dev, (uint32_t)n, k, nullptr, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev));
+    if (rc) return rc;
+    const size_t bytes = 8 + 12 * (size_t)k;
+    CK(cudaMemcpyAsync(s->res_pin, s->res_dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const uint32_t nf = *reinterpret_cast<uint32_t *>(s->res_pin);
+    *n_found = nf;
+    memcpy(row_ids, s->res_pin + 8, nf * sizeof(uint64_t));
+    memcpy(scores, s->res_pin + 8 + 8 * (size_t)k, nf * sizeof(float));
+    return SEMA_OK;
+}
+
+int sema_index_search_batch(sema_index *s, const float *Q, uint32_t nq, uint32_t k,
+                            uint64_t *row_ids, float *scores, uint32_t *n_found)
+{
+    if (!s || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
+    if (nq && !Q) return fail(SEMA_ERR_INVALID, "null queries");
+    if (k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u > SEMA_MAX_K %u", k, SEMA_MAX_K);
+    if (k && nq && (!row_ids || !scores)) return fail(SEMA_ERR_INVALID, "null output");
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    for (uint32_t i = 0; i < nq; ++i) n_found[i] = 0;
+    if (k == 0 || n == 0 || nq == 0) return SEMA_OK;
+    rc = ensure(reinterpret_cast<void **>(&s->Q_dev), &s->batch_cap_q, (size_t)nq * s->ld * sizeof(float));
+    if (rc) return rc;
+    if (s->batch_cap_res < (size_t)nq * k) {
+        cudaFree(s->bids_dev); cudaFree(s->bsc_dev); cudaFree(s->bnf_dev);
+        s->bids_dev = nullptr; s->bsc_dev = nullptr; s->bnf_dev = nullptr; s->batch_cap_res = 0;
+        CK(cudaMalloc(&s->bids_dev, (size_t)nq * k * sizeof(uint64_t)));
+        CK(cudaMalloc(&s->bsc_dev, (size_t)nq * k * sizeof(float)));
+        CK(cudaMalloc(&s->bnf_dev, (size_t)nq * sizeof(uint32_t) * (k ? 1 : 1)));
+        s->batch_cap_res = (size_t)nq * k;
+    }
+    if (s->ld != s->dim) CK(cudaMemsetAsync(s->Q_dev, 0, (size_t)nq * s->ld * sizeof(float), s->stream));
+    CK(cudaMemcpy2DAsync(s->Q_dev, s->ld * sizeof(float), Q, s->dim * sizeof(float),
+                         s->dim * sizeof(float), nq, cudaMemcpyHostToDevice, s->stream));
+    for (uint32_t i = 0; i < nq; ++i) {
+        rc = scan_query(s, s->Q_dev + (size_t)i * s->ld, (uint32_t)n, k, nullptr,
+                        s->bids_dev + (size_t)i * k, s->bsc_dev + (size_t)i * k, s->bnf_dev + i);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(row_ids, s->bids_dev, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(scores, s->bsc_dev, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(n_found, s->bnf_dev, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SEMA_OK;
+}
+
+int sema_index_search_keys_device(sema_index *s, const float *q_dev, uint32_t k, uint64_t *keys_dev)
+{
+    if (!s || !q_dev || !keys_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u outside [1, %u]", k, SEMA_MAX_K);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(keys_dev, 0, k * sizeof(uint64_t), s->stream));
+        return SEMA_OK;
+    }
+    const float *qd = q_dev;
+    if (s->ld != s->dim || (reinterpret_cast<uintptr_t>(q_dev) & 15)) {
+        CK(cudaMemcpyAsync(s->q_dev, q_dev, s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        qd = s->q_dev;
+    }
+    return scan_query(s, qd, (uint32_t)n, k, keys_dev, nullptr, nullptr, nullptr);
+}
+
+int sema_index_search_device(sema_index *s, const float *q_dev, uint32_t k, uint64_t *ids_dev,
+                             float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u outside [1, %u]", k, SEMA_MAX_K);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(n_found_dev, 0, sizeof(uint32_t), s->stream));
+        return SEMA_OK;
+    }
+    const float *qd = q_dev;
+    if (s->ld != s->dim || (reinterpret_cast<uintptr_t>(q_dev) & 15)) {
+        CK(cudaMemcpyAsync(s->q_dev, q_dev, s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        qd = s->q_dev;
+    }
+    return scan_query(s, qd, (uint32_t)n, k, nullptr, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_topk_merge_device(sema_index *s, const uint64_t *keys_dev, uint32_t n_lists, uint32_t k,
+                           uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !keys_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u outside [1, %u]", k, SEMA_MAX_K);
+    if ((uint64_t)n_lists * k > 0x7fffffffull) return fail(SEMA_ERR_INVALID, "too many candidates");
+    CK(cudaSetDevice(s->device));
+    const uint32_t total = n_lists * k;
+    const bool l2 = s->metric == SEMA_METRIC_L2;
+    if (k <= (uint32_t)K_PASS)
+        return l2 ? merge_pass_m<METRIC_L2>(s, keys_dev, total, k, nullptr, nullptr, ids_dev, scores_dev, n_found_dev)
+                  : merge_pass_m<METRIC_COSINE>(s, keys_dev, total, k, nullptr, nullptr, ids_dev, scores_dev, n_found_dev);
+    uint64_t *keys = s->keys_dev;
+    for (uint32_t done = 0; done < k; done += K_PASS) {
+        const uint32_t kp = (k - done) < (uint32_t)K_PASS ? (k - done) : (uint32_t)K_PASS;
+        const uint64_t *bound = done ? keys + done - 1 : nullptr;
+        int rc = l2 ? merge_pass_m<METRIC_L2>(s, keys_dev, total, kp, bound, keys + done, nullptr, nullptr, nullptr)
+                    : merge_pass_m<METRIC_COSINE>(s, keys_dev, total, kp, bound, keys + done, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    return decode(s, keys, k, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_index_set_row_base(sema_index *s, uint64_t row_base)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (row_base + s->capacity > 0xfffffffeull) return fail(SEMA_ERR_INVALID, "row_base + capacity must be < 2^32-1");
+    s->row_base = (uint32_t)row_base;
+    return SEMA_OK;
+}
+
+int sema_index_set_stream(sema_index *s, void *cuda_stream, int external)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    s->stream = external ? reinterpret_cast<cudaStream_t>(cuda_stream) : s->own_stream;
+    return SEMA_OK;
+}
+
+uint64_t sema_index_size(const sema_index *s) { return s ? s->n_rows : 0; }
+uint64_t sema_index_visible(sema_index *s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    poll_ingest(s, false);
+    return s->n_visible;
+}
+uint64_t sema_index_capacity(const sema_index *s) { return s ? s->capacity : 0; }
+uint32_t sema_index_dim(const sema_index *s) { return s ? s->dim : 0; }
+int sema_index_device(const sema_index *s) { return s ? s->device : -1; }
+uint64_t sema_index_last_snapshot(const sema_index *s) { return s ? s->last_snapshot : 0; }
+uint64_t sema_index_launch_count(const sema_index *s) { return s ? s->launches : 0; }
+
+int sema_index_set_scan_variant(sema_index *s, int variant)
+{
+    if (!s) return -1;
+    if (variant >= 0) s->variant = variant;
+    return s->variant;
+}
+
+int sema_index_read_rows(sema_index *s, uint64_t first_row, uint64_t n, float *out)
+{
+    if (!s || (n && !out)) return fail(SEMA_ERR_INVALID, "null argument");
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    if (first_row + n > s->n_rows) return fail(SEMA_ERR_INVALID, "rows [%llu, %llu) outside size %llu",
+                                               (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)s->n_rows);
+    if (n == 0) return SEMA_OK;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy2D(out, s->dim * sizeof(float), s->X + first_row * s->ld, s->ld * sizeof(float),
+                    s->dim * sizeof(float), n, cudaMemcpyDeviceToHost));
+    return SEMA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""GpuIndex — thin Python handle over the C ABI (include/sema_b200.h).
+
+Used by the tests, the benchmark and the host-side mirror of the reference's
+storage layer.  All arithmetic happens in the CUDA kernels behind the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import METRIC_COSINE, METRIC_L2, SemaError, check  # noqa: F401
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class GpuIndex:
+    """The chunk-embedding matrix resident in one GPU's HBM.
+
+    Reference counterpart: the ``chunks`` Lance table's ``vector`` column opened by
+    ``LanceIndexer`` (``src/storage/lance_indexer.rs:19-28, 92-101``).
+    """
+
+    def __init__(self, dim: int, capacity_rows: int, device: int = 0, metric: int = METRIC_COSINE):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        check(self._L.sema_index_create(device, dim, capacity_rows, metric, C.byref(self._h)))
+        self.dim = dim
+        self.metric = metric
+        self.device = device
+
+    # -- lifecycle ------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.sema_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    # -- ingest (K1) ------------------------------------------------------------
+    def append(self, rows: np.ndarray, valid: np.ndarray | None = None, normalize: bool = True,
+               asynchronous: bool = False) -> int:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"rows must be [n, {self.dim}], got {rows.shape}")
+        v = None
+        if valid is not None:
+            v = np.ascontiguousarray(valid, dtype=np.uint8)
+            if v.shape != (rows.shape[0],):
+                raise ValueError("valid must hold one byte per row")
+        first = C.c_uint64()
+        fn = self._L.sema_index_append_async if asynchronous else self._L.sema_index_append
+        check(fn(self._h, _ptr(rows), rows.shape[0], _ptr(v), int(normalize), C.byref(first)))
+        if asynchronous:
+            self._keepalive = getattr(self, "_keepalive", []) + [rows, v]
+        return first.value
+
+    def flush(self) -> None:
+        check(self._L.sema_index_flush(self._h))
+        self._keepalive = []
+
+    def append_device(self, rows_ptr: int, n: int, valid_ptr: int | None = None,
+                      normalize: bool = True) -> int:
+        first = C.c_uint64()
+        check(self._L.sema_index_append_device(self._h, C.c_void_p(rows_ptr), n,
+                                               C.c_void_p(valid_ptr) if valid_ptr else None,
+                                               int(normalize), C.byref(first)))
+        return first.value
+
+    def append_synthetic(self, seed: int, row0: int, n: int, normalize: bool = True) -> int:
+        first = C.c_uint64()
+        check(self._L.sema_index_append_synthetic(self._h, seed, row0, n, int(normalize), C.byref(first)))
+        return first.value
+
+    def tombstone(self, rows) -> None:
+        r = np.ascontiguousarray(rows, dtype=np.uint64)
+        check(self._L.sema_index_tombstone(self._h, _ptr(r), r.shape[0]))
+
+    # -- search (K2 / K3) -----------------------------------------------------------
+    def search(self, q: np.ndarray, k: int):
+        """-> (row_ids uint64[n_found], scores float32[n_found]) best first."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.shape != (self.dim,):
+            raise ValueError(f"query must be [{self.dim}], got {q.shape}")
+        ids = np.zeros(max(k, 1), dtype=np.uint64)
+        sc = np.zeros(max(k, 1), dtype=np.float32)
+        nf = C.c_uint32()
+        check(self._L.sema_index_search(self._h, _ptr(q), k, _ptr(ids), _ptr(sc), C.byref(nf)))
+        return ids[:nf.value].copy(), sc[:nf.value].copy()
+
+    def search_into(self, q: np.ndarray, k: int, ids: np.ndarray, sc: np.ndarray) -> int:
+        """Allocation-free variant for timing loops; returns n_found."""
+        nf = C.c_uint32()
+        check(self._L.sema_index_search(self._h, _ptr(q), k, _ptr(ids), _ptr(sc), C.byref(nf)))
+        return nf.value
+
+    def search_batch(self, Q: np.ndarray, k: int):
+        """-> (row_ids uint64[nq,k], scores float32[nq,k], n_found uint32[nq])."""
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        if Q.ndim != 2 or Q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [nq, {self.dim}], got {Q.shape}")
+        nq = Q.shape[0]
+        ids = np.zeros((nq, max(k, 1)), dtype=np.uint64)
+        sc = np.zeros((nq, max(k, 1)), dtype=np.float32)
+        nf = np.zeros(max(nq, 1), dtype=np.uint32)
+        check(self._L.sema_index_search_batch(self._h, _ptr(Q), nq, k, _ptr(ids), _ptr(sc), _ptr(nf)))
+        return ids, sc, nf[:nq]
+
+    def search_keys_device(self, q_ptr: int, k: int, keys_ptr: int) -> None:
+        check(self._L.sema_index_search_keys_device(self._h, C.c_void_p(q_ptr), k, C.c_void_p(keys_ptr)))
+
+    def search_device(self, q_ptr: int, k: int, ids_ptr: int, scores_ptr: int, nfound_ptr: int) -> None:
+        check(self._L.sema_index_search_device(self._h, C.c_void_p(q_ptr), k, C.c_void_p(ids_ptr),
+                                               C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))
+
+    def merge_device(self, keys_ptr: int, n_lists: int, k: int, ids_ptr: int, scores_ptr: int,
+                     nfound_ptr: int) -> None:
+        check(self._L.sema_topk_merge_device(self._h, C.c_void_p(keys_ptr), n_lists, k,
+                                             C.c_void_p(ids_ptr), C.c_void_p(scores_ptr),
+                                             C.c_void_p(nfound_ptr)))
+
+    # -- properties -------------------------------------------------------------------
+    def set_row_base(self, base: int) -> None:
+        check(self._L.sema_index_set_row_base(self._h, base))
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """Run searches on the caller's stream (an int cudaStream_t handle; 0 = the CUDA
+        default stream) or, with None, on the handle's own query stream."""
+        if cuda_stream is None:
+            check(self._L.sema_index_set_stream(self._h, None, 0))
+        else:
+            check(self._L.sema_index_set_stream(self._h, C.c_void_p(cuda_stream), 1))
+
+    def set_scan_variant(self, variant: int) -> int:
+        return self._L.sema_index_set_scan_variant(self._h, variant)
+
+    def __len__(self) -> int:
+        return int(self._L.sema_index_size(self._h))
+
+    @property
+    def visible(self) -> int:
+        return int(self._L.sema_index_visible(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(self._L.sema_index_capacity(self._h))
+
+    @property
+    def last_snapshot(self) -> int:
+        return int(self._L.sema_index_last_snapshot(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.sema_index_launch_count(self._h))
+
+    def read_rows(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), dtype=np.float32)
+        check(self._L.sema_index_read_rows(self._h, first, n, _ptr(out)))
+        return out

@@ -1,0 +1,20 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 via gpurun)")
+
+
+@pytest.fixture(scope="session")
+def oracle_c():
+    """The C restatement (oracle/cpu_scan.c), built on demand."""
+    from oracle import c_oracle
+    c_oracle.build()
+    return c_oracle

@@ -1,0 +1,373 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle.
+
+Acceptance rule (BASELINE.json): identical top-k id set and order except for ties
+within 1e-5; scores within 1e-5 relative (oracle.check_parity).  Exact-tie cases and
+row ids are checked bit-exactly.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def sema():
+    import sema_b200
+    from sema_b200 import _lib
+    if _lib.lib().sema_device_count() == 0:
+        pytest.fail("gpu-marked test run without a CUDA device")
+    return sema_b200
+
+
+def _unit(seed, n, d):
+    return O.normalize(O.synth(seed, 0, n, d))
+
+
+# ---------------------------------------------------------------- K1 ingest
+@pytest.mark.parametrize("d", [384, 768, 130, 50, 4, 1])
+def test_k1_normalize_matches_reference_rule(sema, d):
+    # src/semantic/embeddings.rs:83-88
+    n = 257
+    raw = O.synth(21, 0, n, d)
+    raw[3] = 0.0
+    if d >= 2:
+        raw[4] = 0.0
+        raw[4, :2] = [3.0, 4.0]
+    with sema.GpuIndex(d, n) as idx:
+        assert idx.append(raw, normalize=True) == 0
+        got = idx.read_rows(0, n)
+    want = O.normalize(raw)
+    assert np.array_equal(got[3], np.zeros(d, np.float32))     # zero row stays zero
+    if d >= 2:
+        assert np.array_equal(got[4, :2], np.array([3.0, 4.0], np.float32) / np.float32(5.0))
+    # only the summation order differs from the sequential reference sum
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
+
+
+def test_k1_no_normalize_is_bit_exact_copy(sema):
+    X = _unit(5, 300, 384)
+    with sema.GpuIndex(384, 300) as idx:
+        idx.append(X, normalize=False)
+        assert np.array_equal(idx.read_rows(0, 300), X)
+
+
+def test_k1_synthetic_generator_is_bit_identical_to_oracle(sema):
+    with sema.GpuIndex(384, 1000) as idx:
+        idx.append_synthetic(seed=1, row0=12345, n=1000, normalize=False)
+        assert np.array_equal(idx.read_rows(0, 1000), O.synth(1, 12345, 1000, 384))
+
+
+# ---------------------------------------------------------------- K2 scan
+CASES = [
+    # n, d, k
+    (1, 384, 10), (3, 384, 1), (31, 384, 10), (33, 384, 50), (1000, 384, 10), (4097, 384, 50),
+    (50001, 384, 10), (50001, 384, 100), (20000, 384, 128), (20000, 768, 100), (5000, 768, 10),
+    (3000, 130, 50), (3000, 50, 10), (2000, 1024, 10), (500, 2048, 33), (2000, 4, 10),
+    (6000, 384, 200), (6000, 384, 1024),
+]
+
+
+@pytest.mark.parametrize("metric", [0, 1], ids=["cosine", "l2"])
+@pytest.mark.parametrize("n,d,k", CASES)
+def test_k2_search_matches_oracle(sema, oracle_c, n, d, k, metric):
+    X = _unit(1, n, d)
+    Q = _unit(2, 3, d)
+    with sema.GpuIndex(d, n + 5, metric=metric) as idx:
+        idx.append(X, normalize=False)         # bit-identical matrix on both sides
+        for q in Q:
+            ids, sc = idx.search(q, k)
+            r_ids, r_sc = oracle_c.scan(X, q, k, metric)
+            assert len(ids) == min(k, n)
+            O.check_parity(ids, sc, r_ids, r_sc)
+            # ranking direction
+            assert np.all(np.diff(sc) >= 0) if metric else np.all(np.diff(sc) <= 0)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_k2_variants_agree(sema, oracle_c, variant):
+    n, d = 30011, 384
+    X = _unit(3, n, d)
+    q = _unit(4, 1, d)[0]
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        idx.set_scan_variant(variant)
+        ids, sc = idx.search(q, 10)
+    r_ids, r_sc = oracle_c.scan(X, q, 10)
+    O.check_parity(ids, sc, r_ids, r_sc)
+
+
+def test_empty_index_and_k_zero(sema):
+    # missing table => Ok(empty) (src/storage/lance_indexer.rs:108-111)
+    with sema.GpuIndex(384, 10) as idx:
+        ids, sc = idx.search(np.zeros(384, np.float32), 10)
+        assert len(ids) == 0 and len(sc) == 0
+        idx.append(_unit(1, 4, 384), normalize=False)
+        ids, _ = idx.search(np.zeros(384, np.float32), 0)
+        assert len(ids) == 0
+
+
+def test_limit_larger_than_table(sema, oracle_c):
+    X = _unit(1, 7, 384)
+    with sema.GpuIndex(384, 7) as idx:
+        idx.append(X, normalize=False)
+        ids, sc = idx.search(X[2].copy(), 50)      # SEARCH_RESULTS_LIMIT = 50, src/tui/engine.rs:11
+    r_ids, r_sc = oracle_c.scan(X, X[2].copy(), 50)
+    assert len(ids) == 7 and ids[0] == 2
+    O.check_parity(ids, sc, r_ids, r_sc)
+
+
+def test_null_and_nonfinite_rows_never_returned(sema, oracle_c):
+    # nullable vector column: src/storage/lance_indexer.rs:41-45, 66-70
+    n, d = 2000, 384
+    raw = O.synth(9, 0, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::7] = 0
+    raw[11, 5] = np.nan
+    raw[13, 0] = np.inf
+    ok = valid.copy()
+    ok[11] = ok[13] = 0
+    q = O.normalize(raw[14:15].copy())[0]          # 14 is a null row (14 % 7 == 0): must not match itself
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(raw, valid=valid, normalize=True)
+        ids, sc = idx.search(q, 100)
+        all_ids, _ = idx.search(q, 1024)
+        X = idx.read_rows(0, n)
+    assert not (set(ids.tolist()) & set(np.nonzero(ok == 0)[0].tolist()))
+    assert np.isnan(X[0]).all() and np.isnan(X[11]).all()
+    Xo = O.normalize(np.where(ok[:, None] == 1, raw, 0).astype(np.float32))
+    r_ids, r_sc = oracle_c.scan(Xo, q, 100, valid=ok)
+    O.check_parity(ids, sc, r_ids, r_sc)
+    assert len(all_ids) == min(1024, int(ok.sum()))
+
+
+def test_all_rows_null(sema):
+    raw = O.synth(9, 0, 64, 384)
+    with sema.GpuIndex(384, 64) as idx:
+        idx.append(raw, valid=np.zeros(64, np.uint8))
+        ids, _ = idx.search(O.normalize(raw[:1])[0], 10)
+        assert len(ids) == 0
+
+
+def test_exact_ties_rank_lower_row_id_first(sema):
+    n, d = 5000, 384
+    X = _unit(1, n, d)
+    for r in (4000, 17, 2500, 4999):
+        X[r] = X[100]
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        ids, sc = idx.search(X[100].copy(), 6)
+    assert ids[:5].tolist() == [17, 100, 2500, 4000, 4999]
+    assert len(set(sc[:5].tolist())) == 1
+
+
+def test_metric_equivalence_l2_vs_cosine(sema):
+    # LanceDB default L2 over unit rows orders like cosine; _distance = 2 - 2 cos
+    n, d, k = 20000, 384, 50
+    X = _unit(1, n, d)
+    q = _unit(2, 1, d)[0]
+    with sema.GpuIndex(d, n, metric=0) as a, sema.GpuIndex(d, n, metric=1) as b:
+        a.append(X, normalize=False)
+        b.append(X, normalize=False)
+        ia, sa = a.search(q, k)
+        ib, sb = b.search(q, k)
+    assert np.array_equal(ia, ib)
+    np.testing.assert_allclose(sb, 2.0 - 2.0 * sa.astype(np.float64), atol=2e-6)
+
+
+def test_l2_metric_on_unnormalised_rows_and_zero_row(sema, oracle_c):
+    # under LanceDB's L2 a zero row has distance |q|^2 = 1 (SURVEY.md §7 edge semantics)
+    n, d = 3000, 384
+    X = (O.synth(1, 0, n, d) / np.float32(65536.0 * 20)).astype(np.float32)
+    X[7] = 0.0
+    q = _unit(2, 1, d)[0]
+    with sema.GpuIndex(d, n, metric=1) as idx:
+        idx.append(X, normalize=False)
+        ids, dist = idx.search(q, 20)
+    r_ids, r_dist = oracle_c.scan(X, q, 20, 1)
+    O.check_parity(ids, dist, r_ids, r_dist)
+
+
+def test_row_base_offsets_ids(sema):
+    X = _unit(1, 100, 384)
+    with sema.GpuIndex(384, 100) as idx:
+        idx.set_row_base(1_000_000)
+        idx.append(X, normalize=False)
+        ids, _ = idx.search(X[42].copy(), 3)
+    assert ids[0] == 1_000_042
+
+
+def test_tombstone_removes_rows(sema, oracle_c):
+    # table.delete(predicate): src/storage/lance_indexer.rs:234-250
+    n, d = 4000, 384
+    X = _unit(1, n, d)
+    q = X[123].copy()
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        ids, _ = idx.search(q, 10)
+        assert ids[0] == 123
+        dead = ids[:3].copy()
+        idx.tombstone(dead)
+        ids2, sc2 = idx.search(q, 10)
+    valid = np.ones(n, np.uint8)
+    valid[dead.astype(np.int64)] = 0
+    r_ids, r_sc = oracle_c.scan(X, q, 10, valid=valid)
+    O.check_parity(ids2, sc2, r_ids, r_sc)
+
+
+def test_append_then_search_sees_new_rows(sema, oracle_c):
+    # table.add then nearest_to: src/storage/lance_indexer.rs:92-95, 121-126
+    d = 384
+    X = _unit(1, 3000, d)
+    q = X[2900].copy()
+    with sema.GpuIndex(d, 3000) as idx:
+        assert idx.append(X[:1000], normalize=False) == 0
+        ids, _ = idx.search(q, 5)
+        assert 2900 not in ids.tolist() and idx.last_snapshot == 1000
+        assert idx.append(X[1000:], normalize=False) == 1000
+        ids, sc = idx.search(q, 5)
+        assert ids[0] == 2900 and idx.last_snapshot == 3000 and len(idx) == 3000
+        r_ids, r_sc = oracle_c.scan(X, q, 5)
+        O.check_parity(ids, sc, r_ids, r_sc)
+        with pytest.raises(sema.SemaError):
+            idx.append(X[:1], normalize=False)       # capacity exceeded
+
+
+def test_async_ingest_snapshot_semantics(sema, oracle_c):
+    # config 5: ingest interleaved with queries; each query equals the oracle on the
+    # snapshot (visible row count) it observed
+    d, batch, nb = 384, 2048, 8
+    X = _unit(1, batch * nb, d)
+    q = _unit(2, 1, d)[0]
+    with sema.GpuIndex(d, batch * nb) as idx:
+        for b in range(nb):
+            idx.append(X[b * batch:(b + 1) * batch], normalize=False, asynchronous=True)
+            ids, sc = idx.search(q, 10)
+            snap = idx.last_snapshot
+            assert snap % batch == 0 and snap <= (b + 1) * batch
+            r_ids, r_sc = oracle_c.scan(X[:snap], q, 10)
+            O.check_parity(ids, sc, r_ids, r_sc)
+        idx.flush()
+        assert idx.visible == batch * nb
+
+
+def test_batch_search_matches_single_queries(sema, oracle_c):
+    n, d, k, nq = 20000, 384, 10, 17
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, k)
+    r_ids, r_sc, r_nf = oracle_c.scan_batch(X, Q, k)
+    assert np.array_equal(nf, r_nf)
+    for i in range(nq):
+        O.check_parity(ids[i], sc[i], r_ids[i], r_sc[i])
+
+
+# ---------------------------------------------------------------- K4 merge
+@pytest.mark.parametrize("G,k", [(2, 10), (8, 10), (8, 100), (4, 300), (3, 1)])
+def test_k4_virtual_shards_equal_single_index(sema, oracle_c, G, k):
+    # G row ranges on one device, allgather replaced by a concatenation
+    import torch
+    n, d = 24000, 384
+    X = _unit(1, n, d)
+    q = _unit(2, 1, d)[0]
+    per = n // G
+    dev = torch.device("cuda:0")
+    q_dev = torch.from_numpy(q).to(dev)
+    keys = torch.zeros(G * k, dtype=torch.int64, device=dev)
+    ids_d = torch.zeros(k, dtype=torch.int64, device=dev)
+    sc_d = torch.zeros(k, dtype=torch.float32, device=dev)
+    nf_d = torch.zeros(1, dtype=torch.int32, device=dev)
+    shards = []
+    try:
+        for g in range(G):
+            lo, hi = g * per, (n if g == G - 1 else (g + 1) * per)
+            s = sema.GpuIndex(d, hi - lo)
+            s.set_row_base(lo)
+            s.append(X[lo:hi], normalize=False)
+            s.set_stream(torch.cuda.current_stream().cuda_stream)
+            shards.append(s)
+        for g, s in enumerate(shards):
+            s.search_keys_device(q_dev.data_ptr(), k, keys.data_ptr() + g * k * 8)
+        shards[0].merge_device(keys.data_ptr(), G, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        for s in shards:
+            s.close()
+    nf = int(nf_d.item())
+    r_ids, r_sc = oracle_c.scan(X, q, k)
+    assert nf == len(r_ids)
+    O.check_parity(ids_d.cpu().numpy().astype(np.uint64)[:nf], sc_d.cpu().numpy()[:nf], r_ids, r_sc)
+
+
+# ---------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_fixtures(sema, path):
+    g = np.load(path)
+    X, Q, valid, k = g["X"], g["Q"], g["valid"], int(g["k"])
+    d = X.shape[1]
+    for metric, tag in ((0, "dot"), (1, "l2")):
+        with sema.GpuIndex(d, X.shape[0], metric=metric) as idx:
+            idx.append(X, valid=valid, normalize=False)
+            for i in range(Q.shape[0]):
+                ids, sc = idx.search(Q[i], k)
+                O.check_parity(ids, sc, g[f"ids_{tag}"][i], g[f"scores_{tag}"][i])
+            ids, sc, nf = idx.search_batch(Q, k)
+            for i in range(Q.shape[0]):
+                O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], g[f"ids_{tag}"][i], g[f"scores_{tag}"][i])
+
+
+# ---------------------------------------------------------------- BASELINE sizes
+def test_config2_1m_x_384_matches_oracle(sema, oracle_c):
+    # BASELINE.json configs[1]: 1M x 384 synthetic unit-norm, single-query top-10.
+    # The corpus is generated on the device and, independently, on the host by the
+    # oracle's generator; K1 and the oracle normalise their own copies.
+    n, d, k = 1_000_000, 384, 10
+    Xo = oracle_c.normalize(oracle_c.synth(1, 0, n, d))
+    Q = oracle_c.normalize(oracle_c.synth(2, 0, 8, d))
+    with sema.GpuIndex(d, n) as idx:
+        idx.append_synthetic(seed=1, row0=0, n=n, normalize=True)
+        for q in Q:
+            ids, sc = idx.search(q, k)
+            r_ids, r_sc = oracle_c.scan(Xo, q, k)
+            O.check_parity(ids, sc, r_ids, r_sc)
+        ids, sc = idx.search(Q[0], 100)
+        r_ids, r_sc = oracle_c.scan(Xo, Q[0], 100)
+        O.check_parity(ids, sc, r_ids, r_sc)
+
+
+def test_full_size_10m_x_384_properties(sema, oracle_c):
+    # BASELINE.json headline size.  Size-independent properties:
+    #  (1) a stored row used as the query returns itself first with score ~ 1;
+    #  (2) the result over N rows equals the K4 merge of results over row sub-ranges
+    #      (checked through the oracle on the rows the GPU returned);
+    #  (3) every returned score equals the oracle's fp32 dot on that row (regenerated
+    #      on the host from the row id alone) and the list is sorted.
+    n, d, k = 10_000_000, 384, 10
+    Q = oracle_c.normalize(oracle_c.synth(2, 0, 4, d))
+    Xo = oracle_c.normalize(oracle_c.synth(1, 0, 1_000_000, d))
+    with sema.GpuIndex(d, n) as idx:
+        idx.append_synthetic(seed=1, row0=0, n=n, normalize=True)
+        for probe in (0, 1, 4_999_999, n - 1):
+            ids, sc = idx.search(idx.read_rows(probe, 1)[0], 3)
+            assert ids[0] == probe and abs(sc[0] - 1.0) < 1e-5
+        for q in Q:
+            ids, sc = idx.search(q, k)
+            assert len(ids) == k and np.all(np.diff(sc) <= 0) and len(set(ids.tolist())) == k
+            for i, s in zip(ids, sc):
+                row = oracle_c.normalize(oracle_c.synth(1, int(i), 1, d))
+                want = O.row_keys(row, q)[0]
+                assert abs(s - want) <= 1e-5 * abs(want)
+            # the first 1M-row prefix: every oracle hit that beats the GPU's k-th score
+            # must be in the GPU list (no better row was missed in that prefix)
+            p_ids, p_sc = oracle_c.scan(Xo, q, k)
+            for i, s in zip(p_ids, p_sc):
+                if s > sc[-1] + 1e-5:
+                    assert i in ids
