@@ -92,9 +92,22 @@ int sema_index_tombstone(sema_index *idx, const uint64_t *rows, uint64_t n);
  * index is SEMA_OK with *n_found = 0 (:108-111). */
 int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row_ids,
                       float *scores, uint32_t *n_found);
-/* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq]. */
+/* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq].  With the
+ * cosine metric, dim % 64 == 0, dim <= 384, k <= 100 and nq >= 4 this runs kernel K3 (tcgen05
+ * tensor cores, bf16x3 split precision, exact fp32 re-scoring of the candidates; needs a second
+ * dim*4 bytes per row of HBM for the bf16 planes, built on first use); otherwise, or if that
+ * memory cannot be had, K2 runs once per query.  Results are identical either way. */
 int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32_t k,
                             uint64_t *row_ids, float *scores, uint32_t *n_found);
+/* Same with queries and results resident on the device (Q_dev: nq x dim dense). */
+int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
+                                   uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
+/* mode 0 = automatic, 1 = always K2 per query, 2 = K3 whenever the shape allows; other values
+ * only query.  Returns the mode now active. */
+int sema_index_set_batch_mode(sema_index *idx, int mode);
+/* queries served by K3 so far, and how many of them were re-run through K2 because exactness
+ * could not be proven from the candidate lists (heavy ties / duplicates). */
+int sema_index_batch_stats(const sema_index *idx, uint64_t *k3_queries, uint64_t *k3_fallbacks);
 
 /* ---- device-resident variants (no host copies, no synchronisation) --------
  * Used for kernel-only timing and by the sharded path.  q_dev: dim floats on the

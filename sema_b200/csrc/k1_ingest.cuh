@@ -47,7 +47,7 @@ synth_kernel(float *dst, uint32_t ld, uint32_t d, uint64_t seed, uint64_t row0, 
 template <bool VEC4>
 __global__ void __launch_bounds__(INGEST_THREADS)
 ingest_kernel(const float *src, uint64_t src_ld, float *dst, uint32_t ld, uint32_t d, uint64_t n,
-              const uint8_t *valid_in, uint8_t *valid_out, int normalize)
+              const uint8_t *valid_in, uint8_t *valid_out, int normalize, float *max_norm2)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -98,7 +98,11 @@ ingest_kernel(const float *src, uint64_t src_ld, float *dst, uint32_t ld, uint32
             }
         }
         __syncwarp();
-        if (lane == 0) valid_out[r] = ok ? 1 : 0;
+        if (lane == 0) {
+            valid_out[r] = ok ? 1 : 0;
+            // non-negative floats order like unsigned ints; K3 uses this to bound |x|
+            if (ok) atomicMax(reinterpret_cast<unsigned int *>(max_norm2), __float_as_uint(scale ? 1.0000005f : ss));
+        }
     }
 }
 

@@ -1,0 +1,488 @@
+// k3_batch.cuh — kernel K3: batched multi-query scan on the tcgen05 tensor cores.
+//
+// The reference issues table.query().nearest_to(q)?.limit(k) once per query
+// (src/storage/lance_indexer.rs:121-126); Q queries against the same table are a dense
+// contraction S = Q . X^T (Q x N x d), so this path runs it on the 5th-gen tensor
+// cores with error-compensated split precision and a fused per-query selection:
+//
+//   x = x_hi + x_lo, q = q_hi + q_lo (bf16 each, round-to-nearest residuals)
+//   S ~= q_hi.x_hi + q_lo.x_hi + q_hi.x_lo     (3 x kind::f16 UMMA, fp32 accumulate in TMEM)
+//   |S - q.x| <= 3*2^-16 |q||x| + fp32 accumulation error  (dropped terms are O(2^-16))
+//
+// The tensor-core pass only *selects* candidates (KC >= k per query and row partition);
+// k3_rescore_kernel then recomputes the candidates' scores in plain fp32 with K2's
+// arithmetic, ranks them exactly and proves, per query, that no row outside the candidate
+// lists can reach the k-th exact score (else the query is flagged and the host re-runs it
+// through K2).  Results are therefore exactly K2's.
+//
+// Layout.  A CTA owns one tile of 128 queries — the UMMA A operand, kept resident in
+// TMEM for the CTA's lifetime (row m <-> TMEM lane m, 2 bf16 per 32-bit column: q_hi in
+// columns [0,192), q_lo in [192,384) for d = 384) — and streams a contiguous range of
+// 64-row corpus tiles (the B operand) through a shared-memory ring with 1-D bulk async
+// copies (TMA, cp.async.bulk + mbarrier complete_tx).  The corpus planes are stored in
+// HBM already in the UMMA canonical K-major no-swizzle core-matrix order, so a stage is
+// one contiguous 16 KB copy and needs no tensor map: per 64-row tile, per 64-wide k
+// block: [hi | lo][k-chunk of 8 elements (8)][row group (8)][row in group (8)][8 bf16].
+// Two 128x64 fp32 accumulators (TMEM columns [384,448) and [448,512)) double-buffer the
+// MMA against the epilogue.  Each epilogue thread owns one query (= one TMEM lane): it
+// reads its 64 scores with tcgen05.ld and keeps a private candidate list in shared memory.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "k2_scan.cuh"
+
+namespace sema {
+namespace k3 {
+
+constexpr int TILE_Q = 128;            // queries per CTA (UMMA M)
+constexpr int TILE_N = 64;             // corpus rows per accumulator tile (UMMA N)
+constexpr int BLOCK_K = 64;            // k elements per pipeline stage
+constexpr int UMMA_K = 16;             // k per tcgen05.mma (bf16)
+constexpr int STAGE_PLANE_BYTES = TILE_N * BLOCK_K * 2;   // 8 KB: one plane of one stage
+constexpr int STAGE_BYTES = 2 * STAGE_PLANE_BYTES;        // hi + lo = 16 KB
+constexpr int THREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int MAX_DIM = 384;           // q_hi + q_lo need dim columns; 128 are the accumulators
+
+// bytes of the pre-tiled planes per 64-row tile
+__host__ __device__ constexpr size_t tile_bytes(int dim) { return (size_t)TILE_N * dim * 4; }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]   (M=128, N=64, K=16, bf16 x bf16 -> f32)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous (128 B).
+//   LBO = byte distance between the two 16-byte k-chunks of one K=16 step
+//   SBO = byte distance between consecutive 8-row groups
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
+}
+
+// instruction descriptor: c=f32, a=b=bf16, both K-major, M=128, N=64, dense
+__host__ __device__ constexpr uint32_t make_idesc()
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_Q >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem)
+{
+    const uint32_t a = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo_elem));
+    const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi_elem));
+    return a | (b << 16);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// ---------------------------------------------------------------- plane builder
+// X (fp32, row stride ld) rows [row_begin, row_end) -> pre-tiled bf16 hi/lo planes.
+// One thread per (row, 8-element k-chunk); consecutive threads write consecutive 16 B.
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float *X, uint32_t ld, uint32_t dim, uint64_t row_begin, uint64_t row_end,
+                    uint64_t n_valid_rows, unsigned char *planes)
+{
+    const uint32_t chunks = dim / 8;
+    const uint64_t total = (row_end - row_begin) * chunks;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        // i -> (tile-relative) ordering: r%8 fastest, then r/8 (within tile), then chunk, then tile
+        const uint64_t rows_span = row_end - row_begin;  // multiple of TILE_N by construction
+        (void)rows_span;
+        const uint64_t t = i / ((uint64_t)TILE_N * chunks);
+        const uint32_t w = (uint32_t)(i - t * (uint64_t)TILE_N * chunks);
+        const uint32_t c = w / TILE_N;
+        const uint32_t r = w - c * TILE_N;
+        const uint64_t row = row_begin + t * TILE_N + r;
+        float v[8];
+        if (row < n_valid_rows) {
+            const float4 a = *reinterpret_cast<const float4 *>(X + row * ld + c * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(X + row * ld + c * 8 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.0f;  // padding rows of the last tile
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float h0 = bf16_round(v[2 * e]), h1 = bf16_round(v[2 * e + 1]);
+            hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+            lo[e] = pack_bf16(v[2 * e] - h0, v[2 * e + 1] - h1);
+        }
+        const uint64_t tile = (row_begin / TILE_N) + t;
+        unsigned char *base = planes + tile * tile_bytes((int)dim) + (size_t)(c / 8) * STAGE_BYTES +
+                              (size_t)(c % 8) * (TILE_N * 16) + (size_t)(r / 8) * 128 + (size_t)(r % 8) * 16;
+        *reinterpret_cast<uint4 *>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(base + STAGE_PLANE_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ---------------------------------------------------------------- the batched scan
+struct Params {
+    const unsigned char *planes;  // pre-tiled hi/lo planes
+    const float *Q;               // q_tiles*128 x dim fp32 (zero padded rows)
+    uint32_t *cand_rows;          // [q_tiles*128][parts][KC]  local row ids (0xFFFFFFFF = empty)
+    float *cand_thr;              // [q_tiles*128][parts]      lowest approx score kept (-inf if list not full)
+    uint32_t n_rows;              // visible rows
+    uint32_t n_tiles;             // ceil(n_rows / 64)
+    uint32_t parts;               // row partitions (gridDim.y)
+    uint32_t dim;
+};
+
+template <int KC>
+struct Smem {
+    static constexpr int LIST_BYTES = KC * TILE_Q * 8;     // scores f32 + rows u32
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int STAGES = (227 * 1024 - LIST_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + LIST_BYTES + BAR_BYTES;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(THREADS, 1)
+batch_scan_kernel(const Params p)
+{
+    using S = Smem<KC>;
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *ring = smem;
+    float *list_sc = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);        // [KC][128]
+    uint32_t *list_row = reinterpret_cast<uint32_t *>(list_sc + KC * TILE_Q);       // [KC][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + S::LIST_BYTES);
+    uint64_t *full = bars;                    // [STAGES]  TMA -> MMA
+    uint64_t *empty = bars + STAGES;          // [STAGES]  MMA -> TMA
+    uint64_t *acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
+    uint64_t *acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qt = blockIdx.x, part = blockIdx.y;
+    const uint32_t kblocks = p.dim / BLOCK_K;            // stages per tile
+    const uint32_t acols = p.dim / 2;                    // TMEM columns per query plane
+    // contiguous tile range of this row partition
+    const uint32_t per = (p.n_tiles + p.parts - 1) / p.parts;
+    const uint32_t t0 = min(part * per, p.n_tiles), t1 = min(t0 + per, p.n_tiles);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t acc_col = 2 * acols;      // accumulators follow the two query planes
+
+    // ---- epilogue warps stage the query tile into TMEM (A operand): row m <-> lane m
+    if (warp >= 2) {
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const float *q = p.Q + ((size_t)qt * TILE_Q + m) * p.dim;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+        for (uint32_t c = 0; c < p.dim; c += 16) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 f = *reinterpret_cast<const float4 *>(q + c + 4 * e);
+                v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+                lo[e] = pack_bf16(v[2 * e] - bf16_round(v[2 * e]), v[2 * e + 1] - bf16_round(v[2 * e + 1]));
+            }
+            tmem_st8(lane_addr + c / 2, hi);
+            tmem_st8(lane_addr + acols + c / 2, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ===== TMA producer: one contiguous 16 KB bulk copy per stage =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = t0; t < t1; ++t) {
+                const unsigned char *src = p.planes + (size_t)t * tile_bytes((int)p.dim);
+                for (uint32_t kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    bulk_g2s(ring + stage * STAGE_BYTES, src + (size_t)kb * STAGE_BYTES, STAGE_BYTES, &full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: 3 UMMAs per k-step (hi.hi, lo.hi, hi.lo) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc();
+            uint32_t stage = 0, phase = 0;
+            uint32_t it = 0;
+            for (uint32_t t = t0; t < t1; ++t, ++it) {
+                const uint32_t buf = it & 1, use = it >> 1;
+                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + acc_col + buf * TILE_N;
+                for (uint32_t kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(ring + stage * STAGE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
+                        const uint32_t a_hi = tmem + kb * (BLOCK_K / 2) + j * (UMMA_K / 2);
+                        const uint32_t a_lo = a_hi + acols;
+                        const uint64_t b_hi = make_b_desc(sb + j * 2 * (TILE_N * 16), TILE_N * 16, 128);
+                        const uint64_t b_lo = make_b_desc(sb + STAGE_PLANE_BYTES + j * 2 * (TILE_N * 16), TILE_N * 16, 128);
+                        umma_ts(d_tmem, a_hi, b_hi, idesc, (kb | j) != 0);
+                        umma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                        umma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                    }
+                    umma_commit(&empty[stage]);          // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[buf]);             // accumulator ready for the epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: thread m owns query m; private candidate list in shared memory =====
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + acc_col;
+        float thr = -INFINITY;   // lowest score kept once the list is full
+        int cnt = 0, min_pos = 0;
+        uint32_t it = 0;
+        for (uint32_t t = t0; t < t1; ++t, ++it) {
+            const uint32_t buf = it & 1, use = it >> 1;
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            uint32_t r[2][32];
+            tmem_ld32(lane_addr + buf * TILE_N, r[0]);
+            tmem_ld32(lane_addr + buf * TILE_N + 32, r[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // MMA may overwrite this accumulator
+            const uint32_t row0 = t * TILE_N;
+            // Pass 1 (unrolled, branch-free): which of my 64 scores beat the admission threshold?
+            uint32_t mask[2] = {0u, 0u};
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    mask[h] |= (__uint_as_float(r[h][c]) > thr) ? (1u << c) : 0u;
+            const uint32_t live = p.n_rows - row0;           // rows of this tile that exist (>= 1)
+            if (live < 32) { mask[0] &= (1u << live) - 1u; mask[1] = 0u; }
+            else if (live < 64) mask[1] &= (1u << (live - 32)) - 1u;
+            // Pass 2 (rare, not unrolled: keeps the instruction footprint small): insert them.
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t mk = mask[h];
+#pragma unroll 1
+                while (mk) {
+                    const int c = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) bits = (e == c) ? r[h][e] : bits;   // register select
+                    const float v = __uint_as_float(bits);
+                    if (!(v > thr)) continue;                 // the threshold may have risen meanwhile
+                    const int slot = cnt < KC ? cnt : min_pos;
+                    list_sc[slot * TILE_Q + m] = v;
+                    list_row[slot * TILE_Q + m] = row0 + h * 32 + c;
+                    if (cnt < KC) ++cnt;
+                    if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
+                        float mn = list_sc[m];
+                        int mp = 0;
+#pragma unroll 8
+                        for (int i = 1; i < KC; ++i) {
+                            const float sv = list_sc[i * TILE_Q + m];
+                            if (sv < mn) { mn = sv; mp = i; }
+                        }
+                        thr = mn;
+                        min_pos = mp;
+                    }
+                }
+            }
+        }
+        // publish this partition's candidates for the query
+        const size_t q = (size_t)qt * TILE_Q + m;
+        uint32_t *out = p.cand_rows + (q * p.parts + part) * KC;
+        for (int i = 0; i < KC; ++i) out[i] = i < cnt ? list_row[i * TILE_Q + m] : 0xffffffffu;
+        p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr : -INFINITY;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------- exact fp32 rescoring
+struct RescoreParams {
+    const float4 *X;           // fp32 matrix, row stride ld4
+    const float *Q;            // padded queries, row stride dim
+    const uint32_t *cand_rows; // [q][parts*KC]
+    const float *cand_thr;     // [q][parts]
+    uint64_t *res_ids;         // [nq][k]
+    float *res_scores;         // [nq][k]
+    uint32_t *res_nfound;      // [nq]
+    uint32_t *flags;           // [nq] 1 = exactness not proven, re-run through K2
+    uint32_t ld4, dim, k, parts, kc, row_base;
+    const float *max_norm2;    // device: max squared row norm seen by K1 (bounds |x|)
+    float err_rel;             // |tensor-core score - exact score| <= err_rel * |q| * max|x|
+};
+
+// One block per query: every candidate is re-scored with K2's fp32 arithmetic (lane-strided
+// float4 FMAs + butterfly), ranked by (score, lower row id) and emitted.
+template <int M>
+__global__ void __launch_bounds__(SCAN_THREADS)
+rescore_kernel(const RescoreParams p)
+{
+    __shared__ uint64_t sm_keys[SCAN_WARPS * 32 * M];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x;
+    const int k = (int)p.k;
+    const uint32_t nv = p.dim / 4;  // float4 per row (dim % 64 == 0)
+    const float4 *qp = reinterpret_cast<const float4 *>(p.Q + (size_t)q * p.dim);
+    const uint32_t total = p.parts * p.kc;
+    WarpTopK<M> top;
+    top.init();
+    for (uint32_t i = warp; i < total; i += SCAN_WARPS) {
+        const uint32_t row = p.cand_rows[(size_t)q * total + i];
+        if (row == 0xffffffffu) continue;  // warp-uniform
+        const float4 *xp = p.X + (size_t)row * p.ld4;
+        float acc = 0.0f;
+        for (uint32_t v = lane; v < nv; v += 32) acc = accum4<METRIC_COSINE>(acc, xp[v], qp[v]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
+        const uint64_t key = make_key(acc, p.row_base + row);
+        top.offer(key, lane == 0 && acc == acc, lane, k);
+    }
+    block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
+    if (warp == 0) {
+        emit_results<M, METRIC_COSINE>(top, k, nullptr, p.res_ids + (size_t)q * k, p.res_scores + (size_t)q * k,
+                                       p.res_nfound + q, lane);
+        // exactness proof: rows outside partition P's list have approx score <= thr_P, hence
+        // exact score <= thr_P + err_bound; the k-th exact score must beat that for every P.
+        float worst = -INFINITY;
+        for (uint32_t j = lane; j < p.parts; j += 32) worst = fmaxf(worst, p.cand_thr[(size_t)q * p.parts + j]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) worst = fmaxf(worst, __shfl_xor_sync(FULL, worst, d));
+        const int kj = (k - 1) >> 5, kl = (k - 1) & 31;
+        uint64_t kk = 0;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            if (j == kj) kk = top.v[j];
+        kk = __shfl_sync(FULL, kk, kl);
+        float qq = 0.0f;
+        for (uint32_t v = lane; v < nv; v += 32) qq = accum4<METRIC_COSINE>(qq, qp[v], qp[v]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) qq += __shfl_xor_sync(FULL, qq, d);
+        if (lane == 0) {
+            const float err_bound = p.err_rel * sqrtf(qq) * sqrtf(*p.max_norm2);
+            bool proven = true;
+            if (worst > -INFINITY) proven = (kk != 0) && (key_rank(kk) > worst + err_bound);
+            p.flags[q] = proven ? 0u : 1u;
+        }
+    }
+}
+
+}  // namespace k3
+}  // namespace sema

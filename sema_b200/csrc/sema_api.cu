@@ -17,6 +17,7 @@
 #include "k1_ingest.cuh"
 #include "k2_scan.cuh"
 #include "k4_merge.cuh"
+#include "k3_batch.cuh"
 
 using namespace sema;
 
@@ -82,6 +83,18 @@ struct sema_index {
     std::deque<Pending> pending;
     int variant = 0;
     uint64_t launches = 0;
+    // ---- K3 (batched tensor-core path) state
+    float *max_norm2 = nullptr;         // device: max squared row norm (written by K1)
+    unsigned char *planes = nullptr;    // pre-tiled bf16 hi/lo planes, built lazily
+    uint64_t planes_rows = 0;           // rows [0, planes_rows) are reflected in the planes
+    bool planes_failed = false;         // allocation failed once: stay on the K2 loop
+    float *Qpad_dev = nullptr;
+    uint32_t *cand_rows = nullptr;
+    float *cand_thr = nullptr;
+    uint32_t *flags_dev = nullptr, *flags_pin = nullptr;
+    size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
+    int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 whenever the shape allows
+    uint64_t k3_queries = 0, k3_fallbacks = 0;
 };
 
 namespace {
@@ -251,10 +264,10 @@ int launch_ingest(sema_index *s, const float *src, uint64_t src_ld, uint64_t fir
     if (blocks < 1) blocks = 1;
     if (vec4)
         ingest_kernel<true><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
-            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize);
+            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize, s->max_norm2);
     else
         ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
-            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize);
+            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize, s->max_norm2);
     CK(cudaGetLastError());
     s->launches++;
     return SEMA_OK;
@@ -268,6 +281,166 @@ int publish(sema_index *s, uint64_t n)
     CK(cudaEventRecord(p.ev, s->ingest_stream));
     p.rows_after = s->n_rows;
     s->pending.push_back(p);
+    return SEMA_OK;
+}
+
+
+// ---- K3 dispatch -----------------------------------------------------------------
+constexpr uint32_t K3_MAX_K = 100;
+constexpr float K3_ERR_REL = 2.5e-4f;  // >= 3*2^-16 (dropped split terms) + fp32 accumulation over 3*dim terms
+
+bool k3_shape_ok(const sema_index *s, uint32_t k)
+{
+    return s->metric == SEMA_METRIC_COSINE && s->dim % k3::BLOCK_K == 0 && s->dim <= (uint32_t)k3::MAX_DIM &&
+           k <= K3_MAX_K && !s->planes_failed;
+}
+
+// Bring the bf16 planes up to date with rows [0, n).  Tombstones invalidate from their row on.
+int k3_sync_planes(sema_index *s, uint64_t n)
+{
+    if (!s->planes) {
+        const uint64_t tiles = (s->capacity + k3::TILE_N - 1) / k3::TILE_N;
+        cudaError_t e = cudaMalloc(&s->planes, (size_t)(tiles ? tiles : 1) * k3::tile_bytes((int)s->dim));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            s->planes = nullptr;
+            s->planes_failed = true;  // not an error: the K2 loop serves the batch instead
+            return SEMA_ERR_NOMEM;
+        }
+        s->planes_rows = 0;
+    }
+    if (s->planes_rows >= n) return SEMA_OK;
+    const uint64_t begin = (s->planes_rows / k3::TILE_N) * k3::TILE_N;            // re-tile the partial last tile
+    const uint64_t end = ((n + k3::TILE_N - 1) / k3::TILE_N) * k3::TILE_N;
+    const uint64_t work = (end - begin) * (s->dim / 8);
+    uint64_t blocks = (work + 255) / 256;
+    if (blocks > (uint64_t)s->num_sms * 32) blocks = (uint64_t)s->num_sms * 32;
+    k3::split_planes_kernel<<<(unsigned)blocks, 256, 0, s->stream>>>(s->X, s->ld, s->dim, begin, end, n, s->planes);
+    CK(cudaGetLastError());
+    s->launches++;
+    s->planes_rows = n;
+    return SEMA_OK;
+}
+
+template <int KC>
+int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_tiles)
+{
+    auto kern = k3::batch_scan_kernel<KC>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[s->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC>::TOTAL));
+        attr_set[s->device & 63] = true;
+    }
+    kern<<<dim3(q_tiles, p.parts), k3::THREADS, k3::Smem<KC>::TOTAL, s->stream>>>(p);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+// Qd: nq x dim dense on the device.  Results: device arrays [nq*k], [nq*k], [nq].
+int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+             uint32_t *nf_d)
+{
+    const uint32_t kc = k <= 16 ? 32 : (k <= 48 ? 64 : 128);
+    const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
+    const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
+    int rc;
+    rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, (size_t)q_tiles_all * k3::TILE_Q * s->dim * sizeof(float));
+    if (rc) return rc;
+    if (s->flags_cap < nq) {
+        cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
+        s->flags_dev = nullptr; s->flags_pin = nullptr; s->flags_cap = 0;
+        CK(cudaMalloc(&s->flags_dev, (size_t)nq * sizeof(uint32_t)));
+        CK(cudaHostAlloc(&s->flags_pin, (size_t)nq * sizeof(uint32_t), cudaHostAllocPortable));
+        s->flags_cap = nq;
+    }
+    CK(cudaMemsetAsync(s->Qpad_dev, 0, (size_t)q_tiles_all * k3::TILE_Q * s->dim * sizeof(float), s->stream));
+    CK(cudaMemcpyAsync(s->Qpad_dev, Qd, (size_t)nq * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+
+    // at most num_sms query tiles per launch; the SMs left over become row partitions
+    for (uint32_t qt0 = 0; qt0 < q_tiles_all; qt0 += (uint32_t)s->num_sms) {
+        const uint32_t q_tiles = (q_tiles_all - qt0) < (uint32_t)s->num_sms ? (q_tiles_all - qt0) : (uint32_t)s->num_sms;
+        uint32_t parts = (uint32_t)s->num_sms / q_tiles;
+        if (parts > n_tiles) parts = n_tiles;
+        if (parts < 1) parts = 1;
+        const size_t nqp = (size_t)q_tiles * k3::TILE_Q;
+        rc = ensure(reinterpret_cast<void **>(&s->cand_rows), &s->cand_cap, nqp * parts * kc * sizeof(uint32_t));
+        if (rc) return rc;
+        rc = ensure(reinterpret_cast<void **>(&s->cand_thr), &s->thr_cap, nqp * parts * sizeof(float));
+        if (rc) return rc;
+        k3::Params p;
+        p.planes = s->planes;
+        p.Q = s->Qpad_dev + (size_t)qt0 * k3::TILE_Q * s->dim;
+        p.cand_rows = s->cand_rows;
+        p.cand_thr = s->cand_thr;
+        p.n_rows = n;
+        p.n_tiles = n_tiles;
+        p.parts = parts;
+        p.dim = s->dim;
+        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_tiles) : kc == 64 ? k3_launch_scan<64>(s, p, q_tiles) : k3_launch_scan<128>(s, p, q_tiles);
+        if (rc) return rc;
+        const uint32_t q_first = qt0 * k3::TILE_Q;
+        const uint32_t q_cnt = (nq - q_first) < (uint32_t)nqp ? (nq - q_first) : (uint32_t)nqp;
+        k3::RescoreParams r;
+        r.X = reinterpret_cast<const float4 *>(s->X);
+        r.Q = p.Q;
+        r.cand_rows = s->cand_rows;
+        r.cand_thr = s->cand_thr;
+        r.res_ids = ids_d + (size_t)q_first * k;
+        r.res_scores = sc_d + (size_t)q_first * k;
+        r.res_nfound = nf_d + q_first;
+        r.flags = s->flags_dev + q_first;
+        r.ld4 = s->ld / 4;
+        r.dim = s->dim;
+        r.k = k;
+        r.parts = parts;
+        r.kc = kc;
+        r.row_base = s->row_base;
+        r.max_norm2 = s->max_norm2;
+        r.err_rel = K3_ERR_REL;
+        if (k <= 32) k3::rescore_kernel<1><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        else if (k <= 64) k3::rescore_kernel<2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        else k3::rescore_kernel<4><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        CK(cudaGetLastError());
+        s->launches++;
+    }
+    // queries whose exactness could not be proven (heavy ties / near-duplicates) go through K2
+    CK(cudaMemcpyAsync(s->flags_pin, s->flags_dev, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->k3_queries += nq;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (!s->flags_pin[i]) continue;
+        s->k3_fallbacks++;
+        rc = scan_query(s, s->Qpad_dev + (size_t)i * s->dim, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i);
+        if (rc) return rc;
+    }
+    return SEMA_OK;
+}
+
+// Batched search with the queries already on the device (nq x dim dense).
+int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+               uint32_t *nf_d)
+{
+    const bool want_k3 = s->batch_mode == 2 || (s->batch_mode == 0 && nq >= 4);
+    if (want_k3 && k3_shape_ok(s, k)) {
+        int rc = k3_sync_planes(s, n);
+        if (rc == SEMA_OK) return k3_batch(s, Qd, nq, n, k, ids_d, sc_d, nf_d);
+        if (rc != SEMA_ERR_NOMEM) return rc;
+    }
+    // K2 once per query (still one HBM pass per query)
+    const float *Qp = Qd;
+    if (s->ld != s->dim) {
+        int rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, (size_t)nq * s->ld * sizeof(float));
+        if (rc) return rc;
+        CK(cudaMemsetAsync(s->Qpad_dev, 0, (size_t)nq * s->ld * sizeof(float), s->stream));
+        CK(cudaMemcpy2DAsync(s->Qpad_dev, s->ld * sizeof(float), Qd, s->dim * sizeof(float), s->dim * sizeof(float),
+                             nq, cudaMemcpyDeviceToDevice, s->stream));
+        Qp = s->Qpad_dev;
+    }
+    for (uint32_t i = 0; i < nq; ++i) {
+        int rc = scan_query(s, Qp + (size_t)i * s->ld, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i);
+        if (rc) return rc;
+    }
     return SEMA_OK;
 }
 
@@ -360,6 +533,8 @@ int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metr
     CKD(cudaMalloc(&s->ticket, sizeof(unsigned int)));
     CKD(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
     CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
+    CKD(cudaMalloc(&s->max_norm2, sizeof(float)));
+    CKD(cudaMemset(s->max_norm2, 0, sizeof(float)));
     CKD(cudaMalloc(&s->res_dev, res_bytes));
     CKD(cudaHostAlloc(&s->res_pin, res_bytes, cudaHostAllocPortable));
     CKD(cudaDeviceSynchronize());
@@ -379,6 +554,8 @@ int sema_index_destroy(sema_index *s)
     cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->keys_dev); cudaFree(s->res_dev);
     cudaFreeHost(s->res_pin); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
     cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
+    cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
+    cudaFree(s->cand_thr); cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->ingest_stream) cudaStreamDestroy(s->ingest_stream);
     cudaGetLastError();
@@ -486,6 +663,10 @@ int sema_index_tombstone(sema_index *s, const uint64_t *rows, uint64_t n)
     CK(cudaGetLastError());
     s->launches++;
     CK(cudaStreamSynchronize(s->stream));
+    // the bf16 planes of K3 must forget the dead rows: re-tile from the first one on
+    uint64_t lowest = s->planes_rows;
+    for (uint64_t i = 0; i < n; ++i) if (rows[i] < lowest) lowest = rows[i];
+    s->planes_rows = lowest;
     return SEMA_OK;
 }
 
@@ -532,28 +713,55 @@ int sema_index_search_batch(sema_index *s, const float *Q, uint32_t nq, uint32_t
     s->last_snapshot = n;
     for (uint32_t i = 0; i < nq; ++i) n_found[i] = 0;
     if (k == 0 || n == 0 || nq == 0) return SEMA_OK;
-    rc = ensure(reinterpret_cast<void **>(&s->Q_dev), &s->batch_cap_q, (size_t)nq * s->ld * sizeof(float));
+    rc = ensure(reinterpret_cast<void **>(&s->Q_dev), &s->batch_cap_q, (size_t)nq * s->dim * sizeof(float));
     if (rc) return rc;
     if (s->batch_cap_res < (size_t)nq * k) {
         cudaFree(s->bids_dev); cudaFree(s->bsc_dev); cudaFree(s->bnf_dev);
         s->bids_dev = nullptr; s->bsc_dev = nullptr; s->bnf_dev = nullptr; s->batch_cap_res = 0;
         CK(cudaMalloc(&s->bids_dev, (size_t)nq * k * sizeof(uint64_t)));
         CK(cudaMalloc(&s->bsc_dev, (size_t)nq * k * sizeof(float)));
-        CK(cudaMalloc(&s->bnf_dev, (size_t)nq * sizeof(uint32_t) * (k ? 1 : 1)));
+        CK(cudaMalloc(&s->bnf_dev, (size_t)nq * sizeof(uint32_t)));
         s->batch_cap_res = (size_t)nq * k;
     }
-    if (s->ld != s->dim) CK(cudaMemsetAsync(s->Q_dev, 0, (size_t)nq * s->ld * sizeof(float), s->stream));
-    CK(cudaMemcpy2DAsync(s->Q_dev, s->ld * sizeof(float), Q, s->dim * sizeof(float),
-                         s->dim * sizeof(float), nq, cudaMemcpyHostToDevice, s->stream));
-    for (uint32_t i = 0; i < nq; ++i) {
-        rc = scan_query(s, s->Q_dev + (size_t)i * s->ld, (uint32_t)n, k, nullptr,
-                        s->bids_dev + (size_t)i * k, s->bsc_dev + (size_t)i * k, s->bnf_dev + i);
-        if (rc) return rc;
-    }
+    CK(cudaMemcpyAsync(s->Q_dev, Q, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    rc = batch_core(s, s->Q_dev, nq, (uint32_t)n, k, s->bids_dev, s->bsc_dev, s->bnf_dev);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(row_ids, s->bids_dev, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(scores, s->bsc_dev, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaMemcpyAsync(n_found, s->bnf_dev, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return SEMA_OK;
+}
+
+int sema_index_search_batch_device(sema_index *s, const float *Q_dev, uint32_t nq, uint32_t k,
+                                   uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !Q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K || nq == 0) return fail(SEMA_ERR_INVALID, "k %u / nq %u out of range", k, nq);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(n_found_dev, 0, (size_t)nq * sizeof(uint32_t), s->stream));
+        return SEMA_OK;
+    }
+    return batch_core(s, Q_dev, nq, (uint32_t)n, k, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_index_set_batch_mode(sema_index *s, int mode)
+{
+    if (!s) return -1;
+    if (mode >= 0 && mode <= 2) s->batch_mode = mode;
+    return s->batch_mode;
+}
+
+int sema_index_batch_stats(const sema_index *s, uint64_t *k3_queries, uint64_t *k3_fallbacks)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (k3_queries) *k3_queries = s->k3_queries;
+    if (k3_fallbacks) *k3_fallbacks = s->k3_fallbacks;
     return SEMA_OK;
 }
 

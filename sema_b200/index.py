@@ -123,6 +123,21 @@ class GpuIndex:
         check(self._L.sema_index_search_batch(self._h, _ptr(Q), nq, k, _ptr(ids), _ptr(sc), _ptr(nf)))
         return ids, sc, nf[:nq]
 
+    def search_batch_device(self, q_ptr: int, nq: int, k: int, ids_ptr: int, scores_ptr: int,
+                            nfound_ptr: int) -> None:
+        check(self._L.sema_index_search_batch_device(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(ids_ptr),
+                                                     C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))
+
+    def set_batch_mode(self, mode: int) -> int:
+        """0 = automatic, 1 = K2 once per query, 2 = K3 (tensor cores) whenever the shape allows."""
+        return self._L.sema_index_set_batch_mode(self._h, mode)
+
+    def batch_stats(self) -> tuple[int, int]:
+        """-> (queries served by K3, of which re-run through K2 for lack of an exactness proof)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self._L.sema_index_batch_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def search_keys_device(self, q_ptr: int, k: int, keys_ptr: int) -> None:
         check(self._L.sema_index_search_keys_device(self._h, C.c_void_p(q_ptr), k, C.c_void_p(keys_ptr)))
 

@@ -371,3 +371,108 @@ def test_full_size_10m_x_384_properties(sema, oracle_c):
             for i, s in zip(p_ids, p_sc):
                 if s > sc[-1] + 1e-5:
                     assert i in ids
+
+
+# ---------------------------------------------------------------- K3 batched tensor-core path
+K3_CASES = [
+    # n, nq, k
+    (64, 4, 10), (1000, 17, 10), (50001, 128, 10), (50001, 300, 50), (200000, 64, 100), (20000, 5, 1),
+    (130, 129, 16), (70000, 1024, 10),
+]
+
+
+@pytest.mark.parametrize("n,nq,k", K3_CASES)
+def test_k3_batch_matches_oracle_and_k2(sema, oracle_c, n, nq, k):
+    d = 384
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        assert idx.set_batch_mode(2) == 2                 # tensor-core path
+        ids3, sc3, nf3 = idx.search_batch(Q, k)
+        served, fallbacks = idx.batch_stats()
+        assert served == nq                                # K3 really ran
+        idx.set_batch_mode(1)                              # K2 once per query
+        ids2, sc2, nf2 = idx.search_batch(Q, k)
+    assert np.array_equal(nf3, nf2) and (nf3 == min(k, n)).all()
+    assert np.array_equal(ids3, ids2)
+    assert np.array_equal(sc3, sc2)                        # same fp32 arithmetic after re-scoring
+    r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
+    for i in range(nq):
+        O.check_parity(ids3[i, :nf3[i]], sc3[i, :nf3[i]], r_ids[i, :nf3[i]], r_sc[i, :nf3[i]])
+    assert fallbacks <= max(1, nq // 50)                   # exactness is proven for ~all random queries
+
+
+def test_k3_ties_and_duplicates_fall_back_to_exact_path(sema, oracle_c):
+    # 300 copies of one row: more exact ties than any candidate list holds -> the exactness
+    # proof fails for queries near that row and those queries are re-run through K2
+    n, d, k = 20000, 384, 10
+    X = _unit(1, n, d)
+    X[5000:5300] = X[123]
+    Q = _unit(2, 8, d)
+    Q[0] = X[123]
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        idx.set_batch_mode(2)
+        ids, sc, nf = idx.search_batch(Q, k)
+        served, fallbacks = idx.batch_stats()
+    assert served == 8 and fallbacks >= 1
+    assert ids[0].tolist() == [123] + list(range(5000, 5009))
+    r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
+    for i in range(8):
+        O.check_parity(ids[i], sc[i], r_ids[i], r_sc[i])
+
+
+def test_k3_null_rows_appends_and_tombstones(sema, oracle_c):
+    n, d, k = 30000, 384, 10
+    raw = O.synth(1, 0, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::11] = 0
+    Q = _unit(2, 32, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.set_batch_mode(2)
+        idx.append(raw[:10000], valid=valid[:10000], normalize=True)
+        X = idx.read_rows(0, 10000)
+        ids, sc, nf = idx.search_batch(Q, k)
+        r = oracle_c.scan_batch(np.nan_to_num(X), Q, k, valid=valid[:10000])
+        for i in range(32):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+        # planes follow later appends (the partial last tile is re-tiled) ...
+        idx.append(raw[10000:], valid=valid[10000:], normalize=True)
+        X = idx.read_rows(0, n)
+        ids, sc, nf = idx.search_batch(Q, k)
+        r = oracle_c.scan_batch(np.nan_to_num(X), Q, k, valid=valid)
+        for i in range(32):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+        # ... and tombstones
+        dead = np.unique(ids[:, 0])
+        idx.tombstone(dead)
+        v2 = valid.copy()
+        v2[dead.astype(np.int64)] = 0
+        ids, sc, nf = idx.search_batch(Q, k)
+        r = oracle_c.scan_batch(np.nan_to_num(X), Q, k, valid=v2)
+        for i in range(32):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+        assert idx.batch_stats()[0] == 96
+
+
+def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
+    # dim 768 and the L2 metric are served by K2 (one pass per query): same results
+    X = _unit(1, 5000, 768)
+    Q = _unit(2, 9, 768)
+    with sema.GpuIndex(768, 5000) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, 10)
+        assert idx.batch_stats()[0] == 0
+    r = oracle_c.scan_batch(X, Q, 10)
+    for i in range(9):
+        O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+    X = _unit(1, 5000, 384)
+    Q = _unit(2, 9, 384)
+    with sema.GpuIndex(384, 5000) as idx:                 # auto mode, nq >= 4, cosine -> K3
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, 10)
+        assert idx.batch_stats()[0] == 9
+    r = oracle_c.scan_batch(X, Q, 10)
+    for i in range(9):
+        O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
