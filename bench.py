@@ -50,6 +50,7 @@ def parse():
                     help="single = headline single-query scan (K2); batch = BASELINE config 3, nq-query batches (K3)")
     ap.add_argument("--nq", type=int, default=1024, help="queries per batch (--workload batch)")
     ap.add_argument("--batch-mode", type=int, default=2, help="0 auto, 1 K2 per query, 2 K3 tensor cores")
+    ap.add_argument("--k3-cluster", type=int, default=0, help="K3 cluster size (0 auto, 1, 2, 4) — tuning")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows of the CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -204,6 +205,8 @@ def run_batch(a):
     idx = sema_b200.GpuIndex(a.dim, a.rows, device=0)
     idx.append_synthetic(seed=1, row0=0, n=a.rows, normalize=True)
     idx.set_batch_mode(a.batch_mode)
+    if a.k3_cluster:
+        idx.set_scan_variant(100 + a.k3_cluster)
     with sema_b200.GpuIndex(a.dim, nq, device=0) as qi:
         qi.append(synth_rows(2, 0, nq, a.dim), normalize=True)
         Q = qi.read_rows(0, nq)
@@ -257,7 +260,7 @@ def run_batch(a):
         "unit": "queries/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": dev_ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16x3 split -> f32", "data": "synthetic",
         "config": {"workload": f"{a.rows}x{a.dim} fp32 corpus, batches of {nq} queries, exact top-{k} (BASELINE configs[2])",
-                   "batch_mode": a.batch_mode, "k3_queries": served, "k3_fallback_queries": fallbacks,
+                   "batch_mode": a.batch_mode, "k3_cluster": a.k3_cluster or "auto", "k3_queries": served, "k3_fallback_queries": fallbacks,
                    "l2_flush": "none needed: each batch streams the 15.36 GB bf16 hi/lo planes"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "issued_frac": 3 * achieved / peak, "traffic": None,

@@ -62,7 +62,8 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -71,43 +72,76 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
+    // one asm block with scoped labels: no C-level loop, so the surrounding code stays
+    // warp-uniform for the compiler (uniform registers, no re-convergence scaffolding)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SEMA_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SEMA_DONE;\n\t"
+        "bra SEMA_WAIT;\n\t"
+        "SEMA_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// slice of a stage delivered to the same shared-memory offset of every CTA in cta_mask; each
+// destination CTA's mbarrier (same offset) receives the complete_tx for the bytes it got
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                                   uint16_t cta_mask)
+{
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n\t}"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of cta_mask once the prior MMAs retire
+__device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t cta_mask)
+{
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[tmem] * B[smem]   (M=128, N=64, K=16, bf16 x bf16 -> f32)
+// D[tmem] (+)= A[tmem] * B[smem]   (M=128, N=64, K=16, bf16 x bf16 -> f32).  Called by a
+// converged warp; one elected lane issues.
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate)
 {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -222,7 +256,10 @@ struct Smem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + LIST_BYTES + BAR_BYTES;
 };
 
-template <int KC>
+// C = CTAs per cluster.  The C CTAs of a cluster hold C different query tiles and stream the
+// same corpus tiles: every stage is fetched once per cluster (each CTA issues 1/C of it) and
+// multicast into all C shared memories, cutting the L2->SM operand traffic C-fold.
+template <int KC, int C>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_kernel(const Params p)
 {
@@ -248,7 +285,7 @@ batch_scan_kernel(const Params p)
     const uint32_t t0 = min(part * per, p.n_tiles), t1 = min(t0 + per, p.n_tiles);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], C); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -260,8 +297,15 @@ batch_scan_kernel(const Params p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    if (C > 1) cluster_sync_all();           // every CTA's barriers exist before any remote arrive
+    // The CTA owns all 512 TMEM columns (1 CTA/SM), so the allocation starts at lane 0, column 0;
+    // using the constant keeps every UMMA operand address in uniform registers.
+    if (*tmem_slot != 0) __trap();
+    constexpr uint32_t tmem = 0;
     const uint32_t acc_col = 2 * acols;      // accumulators follow the two query planes
+    const uint32_t crank = C > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t cmask = (uint16_t)((1u << C) - 1u);
+    constexpr uint32_t SLICE = STAGE_BYTES / C;
 
     // ---- epilogue warps stage the query tile into TMEM (A operand): row m <-> lane m
     if (warp >= 2) {
@@ -292,23 +336,29 @@ batch_scan_kernel(const Params p)
     tc_fence_after();
 
     if (warp == 0) {
-        // ===== TMA producer: one contiguous 16 KB bulk copy per stage =====
-        if (lane == 0) {
+        // ===== TMA producer: one contiguous 16 KB bulk copy per stage (whole warp converged,
+        // one elected lane issues) =====
+        {
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = t0; t < t1; ++t) {
                 const unsigned char *src = p.planes + (size_t)t * tile_bytes((int)p.dim);
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait(&empty[stage], phase ^ 1);     // all C consumers released this stage
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    bulk_g2s(ring + stage * STAGE_BYTES, src + (size_t)kb * STAGE_BYTES, STAGE_BYTES, &full[stage]);
+                    if (C == 1)
+                        bulk_g2s(ring + stage * STAGE_BYTES, src + (size_t)kb * STAGE_BYTES, STAGE_BYTES, &full[stage]);
+                    else
+                        bulk_g2s_multicast(ring + stage * STAGE_BYTES + crank * SLICE,
+                                           src + (size_t)kb * STAGE_BYTES + crank * SLICE, SLICE, &full[stage], cmask);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer: 3 UMMAs per k-step (hi.hi, lo.hi, hi.lo) =====
-        if (lane == 0) {
+        // ===== MMA issuer: 3 UMMAs per k-step (hi.hi, lo.hi, hi.lo).  The warp stays converged so
+        // that descriptors and TMEM addresses live in uniform registers; one elected lane issues =====
+        {
             constexpr uint32_t idesc = make_idesc();
             uint32_t stage = 0, phase = 0;
             uint32_t it = 0;
@@ -331,7 +381,8 @@ batch_scan_kernel(const Params p)
                         umma_ts(d_tmem, a_lo, b_hi, idesc, 1);
                         umma_ts(d_tmem, a_hi, b_lo, idesc, 1);
                     }
-                    umma_commit(&empty[stage]);          // frees the smem stage when the MMAs retire
+                    if (C == 1) umma_commit(&empty[stage]);   // frees the smem stage when the MMAs retire
+                    else umma_commit_multicast(&empty[stage], cmask);   // ... in every CTA of the cluster
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&acc_full[buf]);             // accumulator ready for the epilogue
@@ -408,6 +459,7 @@ batch_scan_kernel(const Params p)
 
     tc_fence_before();
     __syncthreads();
+    if (C > 1) cluster_sync_all();           // no CTA leaves while peers may still multicast into it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));

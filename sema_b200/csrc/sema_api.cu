@@ -94,6 +94,7 @@ struct sema_index {
     uint32_t *flags_dev = nullptr, *flags_pin = nullptr;
     size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
     int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 whenever the shape allows
+    int k3_cluster = 0;                 // 0 auto, else forced cluster size (1, 2, 4) — tuning
     uint64_t k3_queries = 0, k3_fallbacks = 0;
 };
 
@@ -322,19 +323,74 @@ int k3_sync_planes(sema_index *s, uint64_t n)
     return SEMA_OK;
 }
 
-template <int KC>
-int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_tiles)
+template <int KC, int C>
+int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_tiles)
 {
-    auto kern = k3::batch_scan_kernel<KC>;
+    auto kern = k3::batch_scan_kernel<KC, C>;
     static bool attr_set[64] = {false};
     if (!attr_set[s->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC>::TOTAL));
         attr_set[s->device & 63] = true;
     }
-    kern<<<dim3(q_tiles, p.parts), k3::THREADS, k3::Smem<KC>::TOTAL, s->stream>>>(p);
-    CK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(q_tiles, p.parts, 1);
+    cfg.blockDim = dim3(k3::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = k3::Smem<KC>::TOTAL;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, p));
     s->launches++;
     return SEMA_OK;
+}
+
+// how many clusters of C CTAs of this kernel can be resident at once (cached per device)
+template <int KC, int C>
+int k3_max_clusters(sema_index *s, int *out)
+{
+    static int cached[64] = {0};
+    int &v = cached[s->device & 63];
+    if (v == 0) {
+        auto kern = k3::batch_scan_kernel<KC, C>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC>::TOTAL));
+        if (C == 1) {
+            v = s->num_sms;
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(C, (unsigned)s->num_sms, 1);
+            cfg.blockDim = dim3(k3::THREADS, 1, 1);
+            cfg.dynamicSmemBytes = k3::Smem<KC>::TOTAL;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = C;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+            v = n > 0 ? n : 1;
+        }
+    }
+    *out = v;
+    return SEMA_OK;
+}
+
+template <int KC>
+int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_tiles, int c)
+{
+    return c == 4 ? k3_launch_scan_c<KC, 4>(s, p, q_tiles)
+         : c == 2 ? k3_launch_scan_c<KC, 2>(s, p, q_tiles) : k3_launch_scan_c<KC, 1>(s, p, q_tiles);
+}
+template <int KC>
+int k3_clusters(sema_index *s, int c, int *out)
+{
+    return c == 4 ? k3_max_clusters<KC, 4>(s, out) : c == 2 ? k3_max_clusters<KC, 2>(s, out) : k3_max_clusters<KC, 1>(s, out);
 }
 
 // Qd: nq x dim dense on the device.  Results: device arrays [nq*k], [nq*k], [nq].
@@ -345,7 +401,8 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
     const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
     int rc;
-    rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, (size_t)q_tiles_all * k3::TILE_Q * s->dim * sizeof(float));
+    const size_t qpad_rows = (size_t)(q_tiles_all + 3) / 4 * 4 * k3::TILE_Q;   // room for cluster padding
+    rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, qpad_rows * s->dim * sizeof(float));
     if (rc) return rc;
     if (s->flags_cap < nq) {
         cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
@@ -354,13 +411,23 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         CK(cudaHostAlloc(&s->flags_pin, (size_t)nq * sizeof(uint32_t), cudaHostAllocPortable));
         s->flags_cap = nq;
     }
-    CK(cudaMemsetAsync(s->Qpad_dev, 0, (size_t)q_tiles_all * k3::TILE_Q * s->dim * sizeof(float), s->stream));
+    CK(cudaMemsetAsync(s->Qpad_dev, 0, qpad_rows * s->dim * sizeof(float), s->stream));
     CK(cudaMemcpyAsync(s->Qpad_dev, Qd, (size_t)nq * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
 
-    // at most num_sms query tiles per launch; the SMs left over become row partitions
-    for (uint32_t qt0 = 0; qt0 < q_tiles_all; qt0 += (uint32_t)s->num_sms) {
-        const uint32_t q_tiles = (q_tiles_all - qt0) < (uint32_t)s->num_sms ? (q_tiles_all - qt0) : (uint32_t)s->num_sms;
-        uint32_t parts = (uint32_t)s->num_sms / q_tiles;
+    // Cluster size C: C query tiles share one stream of corpus tiles (TMA multicast).  The
+    // query-tile count is padded to a multiple of C (Qpad rows beyond nq are zero queries).
+    const int csize = s->k3_cluster > 0 ? s->k3_cluster : (q_tiles_all >= 4 ? 4 : (q_tiles_all >= 2 ? 2 : 1));
+    int max_clusters = 1;
+    rc = kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
+    if (rc) return rc;
+    const uint32_t q_tiles_pad = ((q_tiles_all + csize - 1) / csize) * csize;
+    const uint32_t groups_all = q_tiles_pad / csize;             // clusters along the query axis
+    // at most max_clusters cluster columns per launch; the clusters left over become row partitions
+    for (uint32_t g0 = 0; g0 < groups_all; g0 += (uint32_t)max_clusters) {
+        const uint32_t groups = (groups_all - g0) < (uint32_t)max_clusters ? (groups_all - g0) : (uint32_t)max_clusters;
+        const uint32_t qt0 = g0 * csize;
+        const uint32_t q_tiles = groups * csize;
+        uint32_t parts = (uint32_t)max_clusters / groups;
         if (parts > n_tiles) parts = n_tiles;
         if (parts < 1) parts = 1;
         const size_t nqp = (size_t)q_tiles * k3::TILE_Q;
@@ -377,9 +444,10 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         p.n_tiles = n_tiles;
         p.parts = parts;
         p.dim = s->dim;
-        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_tiles) : kc == 64 ? k3_launch_scan<64>(s, p, q_tiles) : k3_launch_scan<128>(s, p, q_tiles);
+        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_tiles, csize) : kc == 64 ? k3_launch_scan<64>(s, p, q_tiles, csize) : k3_launch_scan<128>(s, p, q_tiles, csize);
         if (rc) return rc;
         const uint32_t q_first = qt0 * k3::TILE_Q;
+        if (q_first >= nq) break;
         const uint32_t q_cnt = (nq - q_first) < (uint32_t)nqp ? (nq - q_first) : (uint32_t)nqp;
         k3::RescoreParams r;
         r.X = reinterpret_cast<const float4 *>(s->X);
@@ -863,6 +931,7 @@ uint64_t sema_index_launch_count(const sema_index *s) { return s ? s->launches :
 int sema_index_set_scan_variant(sema_index *s, int variant)
 {
     if (!s) return -1;
+    if (variant >= 100) { s->k3_cluster = variant - 100; return variant; }   // 100 = auto, 101/102/104 = K3 cluster size
     if (variant >= 0) s->variant = variant;
     return s->variant;
 }
