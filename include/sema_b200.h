@@ -138,6 +138,10 @@ uint64_t sema_index_visible(sema_index *idx);        /* rows a search starting n
 uint64_t sema_index_capacity(const sema_index *idx);
 uint32_t sema_index_dim(const sema_index *idx);
 int sema_index_device(const sema_index *idx);
+/* on != 0: sema_index_search / _search_batch first apply the mean_pool normalise tail
+ * (src/semantic/embeddings.rs:83-88) to the query on the device (kernel K1), as the reference's
+ * embedder does for queries and rows alike.  Returns the setting now active (on < 0 = query). */
+int sema_index_set_normalize_queries(sema_index *idx, int on);
 /* snapshot (visible rows) the most recent search on this handle scanned */
 uint64_t sema_index_last_snapshot(const sema_index *idx);
 /* copy stored (normalised) rows back to the host: out = n x dim floats */

@@ -95,6 +95,8 @@ struct sema_index {
     size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
     int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 whenever the shape allows
     int k3_cluster = 0;                 // 0 auto, else forced cluster size (1, 2, 4) — tuning
+    int normalize_queries = 0;          // apply K1 to host queries before scanning
+    unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch]
     uint64_t k3_queries = 0, k3_fallbacks = 0;
 };
 
@@ -512,6 +514,24 @@ int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t
     return SEMA_OK;
 }
 
+// K1 on query vectors in place (nq rows of `stride` floats on the device, on the query stream)
+int normalize_queries_dev(sema_index *s, float *q, uint64_t stride, uint32_t nq)
+{
+    for (uint32_t done = 0; done < nq; done += 65536) {
+        const uint32_t m = (nq - done) < 65536u ? (nq - done) : 65536u;
+        uint64_t blocks = ((uint64_t)m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+        if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
+        float *base = q + (size_t)done * stride;
+        // generic (scalar) kernel: src == dst, same stride; pad columns [dim, stride) are rewritten as zeros
+        ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(
+            base, stride, base, (uint32_t)stride, s->dim, m, nullptr, s->qscratch,
+            1, reinterpret_cast<float *>(s->qscratch + 65536));
+        CK(cudaGetLastError());
+        s->launches++;
+    }
+    return SEMA_OK;
+}
+
 int check_append(sema_index *s, uint64_t n)
 {
     if (!s) return fail(SEMA_ERR_INVALID, "null index");
@@ -602,6 +622,7 @@ int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metr
     CKD(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
     CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
     CKD(cudaMalloc(&s->max_norm2, sizeof(float)));
+    CKD(cudaMalloc(&s->qscratch, 65536 + 16));
     CKD(cudaMemset(s->max_norm2, 0, sizeof(float)));
     CKD(cudaMalloc(&s->res_dev, res_bytes));
     CKD(cudaHostAlloc(&s->res_pin, res_bytes, cudaHostAllocPortable));
@@ -622,7 +643,7 @@ int sema_index_destroy(sema_index *s)
     cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->keys_dev); cudaFree(s->res_dev);
     cudaFreeHost(s->res_pin); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
     cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
-    cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
+    cudaFree(s->qscratch); cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
     cudaFree(s->cand_thr); cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->ingest_stream) cudaStreamDestroy(s->ingest_stream);
@@ -753,6 +774,10 @@ int sema_index_search(sema_index *s, const float *q, uint32_t k, uint64_t *row_i
     if (k == 0 || n == 0) return SEMA_OK;
     memcpy(s->q_pin, q, s->dim * sizeof(float));
     CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (s->normalize_queries) {
+        rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
+        if (rc) return rc;
+    }
     uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
     float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
     rc = scan_query(s, s->q_dev, (uint32_t)n, k, nullptr, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev));
@@ -792,6 +817,10 @@ int sema_index_search_batch(sema_index *s, const float *Q, uint32_t nq, uint32_t
         s->batch_cap_res = (size_t)nq * k;
     }
     CK(cudaMemcpyAsync(s->Q_dev, Q, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (s->normalize_queries) {
+        rc = normalize_queries_dev(s, s->Q_dev, s->dim, nq);
+        if (rc) return rc;
+    }
     rc = batch_core(s, s->Q_dev, nq, (uint32_t)n, k, s->bids_dev, s->bsc_dev, s->bnf_dev);
     if (rc) return rc;
     CK(cudaMemcpyAsync(row_ids, s->bids_dev, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
@@ -816,6 +845,13 @@ int sema_index_search_batch_device(sema_index *s, const float *Q_dev, uint32_t n
         return SEMA_OK;
     }
     return batch_core(s, Q_dev, nq, (uint32_t)n, k, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_index_set_normalize_queries(sema_index *s, int on)
+{
+    if (!s) return -1;
+    if (on >= 0) s->normalize_queries = on ? 1 : 0;
+    return s->normalize_queries;
 }
 
 int sema_index_set_batch_mode(sema_index *s, int mode)

@@ -128,6 +128,10 @@ class GpuIndex:
         check(self._L.sema_index_search_batch_device(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(ids_ptr),
                                                      C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))
 
+    def set_normalize_queries(self, on: bool) -> int:
+        """Apply the reference's normalise tail (K1) to host queries before scanning."""
+        return self._L.sema_index_set_normalize_queries(self._h, int(on))
+
     def set_batch_mode(self, mode: int) -> int:
         """0 = automatic, 1 = K2 once per query, 2 = K3 (tensor cores) whenever the shape allows."""
         return self._L.sema_index_set_batch_mode(self._h, mode)
