@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries", type=int, default=64, help="distinct query vectors cycled through")
     ap.add_argument("--variant", type=int, default=-1, help="K2 kernel variant (tuning)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: fused = P2P stores + merge inside K2's last block; nccl = all-gather + K4")
     ap.add_argument("--workload", default="single", choices=["single", "batch"],
                     help="single = headline single-query scan (K2); batch = BASELINE config 3, nq-query batches (K3)")
     ap.add_argument("--nq", type=int, default=1024, help="queries per batch (--workload batch)")
@@ -315,10 +317,31 @@ def run_ours(a):
     keys_local = torch.zeros(k, dtype=torch.int64, device=dev)
     keys_all = torch.zeros(world * k, dtype=torch.int64, device=dev)
 
+    group = None
+    exchange = "none"
+    if world > 1:
+        exchange = a.exchange
+        if a.exchange == "fused":
+            try:
+                from sema_b200.sharded import make_shard_group
+                group = make_shard_group(idx, dist)
+            except Exception as e:      # e.g. CUDA IPC not permitted in this container
+                ok = torch.tensor([0], device=dev)
+                exchange = f"nccl (fused unavailable: {e})"
+            else:
+                ok = torch.tensor([1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
+            if int(ok.item()) == 0 and group is not None:
+                group.close()
+                group = None
+                exchange = "nccl (fused unavailable on a peer)"
+
     def step_device(i):
         q = qptr[i % a.queries]
         if world == 1:
             idx.search_device(q, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+        elif group is not None:
+            group.search_device(q, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
         else:
             idx.search_keys_device(q, k, keys_local.data_ptr())
             dist.all_gather_into_tensor(keys_all, keys_local)
@@ -359,6 +382,15 @@ def run_ours(a):
                 idx.search_into(Q[i % a.queries], k, ids_h, sc_h)
             torch.cuda.synchronize()
             e2e_ms = (time.perf_counter() - t0) * 1e3
+        elif group is not None:
+            for i in range(min(a.warmup, 5)):
+                group.search_into(Q[i % a.queries], k, ids_h, sc_h)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(a.steps):
+                group.search_into(Q[i % a.queries], k, ids_h, sc_h)
+            barrier()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
         else:
             from sema_b200.sharded import ShardedSearcher
             sh = ShardedSearcher(idx, dist, k)
@@ -385,6 +417,23 @@ def run_ours(a):
         i = (a.steps - 1) % a.queries
         r_ids, r_sc = idx.search(Q[i], k)
         verified = bool(np.array_equal(ids_d.cpu().numpy().astype(np.uint64), r_ids))
+    elif not a.no_verify:
+        # multi-rank: the fused result must equal the NCCL all-gather + K4 result, and every global
+        # hit that lives on this rank must be this rank's own local hit with the same score
+        from sema_b200.sharded import ShardedSearcher
+        sh = ShardedSearcher(idx, dist, k)
+        verified = True
+        for i in range(4):
+            n_ids, n_sc = sh.search(Q[i])
+            if group is not None:
+                f_ids, f_sc = group.search(Q[i], k)
+                verified &= bool(np.array_equal(f_ids, n_ids) and np.array_equal(f_sc, n_sc))
+            l_ids, l_sc = idx.search(Q[i], k)
+            mine = (n_ids >= lo) & (n_ids < hi)
+            verified &= bool(set(n_ids[mine].tolist()) <= set(l_ids.tolist()))
+        v = torch.tensor([int(verified)], device=dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MIN)
+        verified = bool(v.item())
 
     if rank != 0:
         if dist is not None:
@@ -411,7 +460,8 @@ def run_ours(a):
             "rows_per_gpu": shard_rows, "query_pool": a.queries,
             "l2_flush": f"none needed: each step streams {bytes_per_launch / 1e9:.2f} GB per GPU, "
                         f"{bytes_per_launch / L2_BYTES:.0f}x the 126 MB L2",
-            "parallelism": "single GPU" if world == 1 else f"corpus row-sharded over {world} GPUs, NCCL all-gather of per-shard top-k + K4 merge",
+            "parallelism": "single GPU" if world == 1 else f"corpus row-sharded over {world} GPUs (one process each)",
+            "exchange": exchange if world > 1 else None,
             "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
         },
         "roofline": {
@@ -419,14 +469,15 @@ def run_ours(a):
             "traffic": None, "peak_source": pk_src,
             "kernel": "scan_topk_kernel (K2)",
             "note": "achieved = rows_per_gpu*dim*4 bytes / device time per step (one K2 launch per step"
-                    + ("" if world == 1 else " plus the all-gather and the K4 merge") + ")",
+                    + ("" if world == 1 else ", which includes the top-k exchange and the global merge") + ")",
         },
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": ((a.dim + 3) // 4) * 16,
                 "d2h_bytes_per_step": 8 + 12 * k, "ms_per_step": e2e_ms / a.steps,
-                "path": "sema_index_search (C ABI) with host buffers: query H2D, K2, result D2H, stream sync"},
+                "path": ("sema_index_search" if world == 1 else "sema_shard_group_search" if group is not None else "sharded.ShardedSearcher.search")
+                        + " with host buffers: query H2D, K2 (+ exchange + merge), result D2H, stream sync"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "verified_against_host_api": verified,
+        "verified": verified,
     }
     if world == 1 and not a.no_cpu_baseline:
         try:

@@ -128,6 +128,26 @@ int sema_topk_merge_device(sema_index *idx, const uint64_t *keys_dev, uint32_t n
                            uint32_t k, uint64_t *ids_dev, float *scores_dev,
                            uint32_t *n_found_dev);
 
+/* ---- corpus-sharded group: scan + exchange + merge in ONE kernel per rank -------------
+ * One process per GPU; every rank holds a contiguous row range (sema_index_set_row_base).  The
+ * last block of K2 stores the shard's top-k keys straight into every rank's exchange buffer over
+ * NVLink (peer stores on cudaIpc-mapped memory), raises a flag, waits for all ranks' flags and
+ * merges the world*k keys itself: no NCCL call and no second launch on the query path.  Setup:
+ * create -> local_handle -> (all-gather the 64-byte handles with any transport) -> connect.
+ * Every rank must then issue the same sequence of group searches (SPMD); a missing rank is
+ * reported as an error after ~2 s instead of hanging.  k <= 128. */
+typedef struct sema_shard_group sema_shard_group;
+#define SEMA_IPC_HANDLE_BYTES 64
+#define SEMA_MAX_SHARDS 16
+int sema_shard_group_create(sema_index *idx, uint32_t world, uint32_t rank, sema_shard_group **out);
+int sema_shard_group_local_handle(sema_shard_group *g, void *handle_out /* 64 bytes */);
+int sema_shard_group_connect(sema_shard_group *g, const void *handles /* world x 64 bytes, by rank */);
+int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uint64_t *row_ids,
+                            float *scores, uint32_t *n_found);
+int sema_shard_group_search_device(sema_shard_group *g, const float *q_dev, uint32_t k,
+                                   uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
+int sema_shard_group_destroy(sema_shard_group *g);
+
 /* ---- properties ------------------------------------------------------------ */
 int sema_index_set_row_base(sema_index *idx, uint64_t row_base); /* shard offset of row 0   */
 /* external != 0: run searches on the caller's cudaStream_t `cuda_stream` (0 = the CUDA

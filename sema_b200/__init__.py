@@ -6,6 +6,6 @@ Importing the package does not load the library; the first use does, and fails
 loudly when it has not been built (there is no CPU fallback).
 """
 from ._lib import METRIC_COSINE, METRIC_L2, SemaError  # noqa: F401
-from .index import GpuIndex  # noqa: F401
+from .index import GpuIndex, ShardGroup  # noqa: F401
 
-__all__ = ["GpuIndex", "SemaError", "METRIC_COSINE", "METRIC_L2"]
+__all__ = ["GpuIndex", "ShardGroup", "SemaError", "METRIC_COSINE", "METRIC_L2"]

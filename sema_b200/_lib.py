@@ -49,6 +49,12 @@ SIGNATURES = {
     "sema_index_search_keys_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "sema_index_search_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
     "sema_topk_merge_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
+    "sema_shard_group_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "sema_shard_group_local_handle": (C.c_int, [_vp, _vp]),
+    "sema_shard_group_connect": (C.c_int, [_vp, _vp]),
+    "sema_shard_group_search": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _u32p]),
+    "sema_shard_group_search_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
+    "sema_shard_group_destroy": (C.c_int, [_vp]),
     "sema_index_set_row_base": (C.c_int, [_vp, C.c_uint64]),
     "sema_index_set_stream": (C.c_int, [_vp, _vp, C.c_int]),
     "sema_index_size": (C.c_uint64, [_vp]),

@@ -20,6 +20,38 @@ namespace sema {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 
+// Peer exchange of the corpus-sharded mode, fused into K2's last block: every rank stores its
+// local top-k keys straight into every rank's exchange buffer over NVLink (P2P stores on
+// cudaIpc-mapped memory), raises a per-(slot, source) flag with release.sys, then waits for all
+// ranks' flags and merges the world*k keys itself — scan + exchange + merge in ONE launch per rank.
+constexpr int XCHG_MAX_WORLD = 16;
+constexpr int XCHG_KEYS = 128;   // keys per (slot, source rank)
+struct Exchange {
+    uint64_t *peer[XCHG_MAX_WORLD];  // peer[g]: rank g's buffer as mapped in this process (peer[rank] = own)
+    uint32_t world;                  // 0 = exchange disabled (plain single-index search)
+    uint32_t rank;
+    uint64_t seq;                    // search sequence number, identical on all ranks, starts at 1
+    // buffer layout (uint64 units): keys[2][world][XCHG_KEYS], then flags[2][world]
+};
+__device__ __forceinline__ uint64_t *xchg_keys(uint64_t *buf, uint32_t world, uint32_t slot, uint32_t src)
+{
+    return buf + ((size_t)slot * world + src) * XCHG_KEYS;
+}
+__device__ __forceinline__ uint64_t *xchg_flag(uint64_t *buf, uint32_t world, uint32_t slot, uint32_t src)
+{
+    return buf + (size_t)2 * world * XCHG_KEYS + (size_t)slot * world + src;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct ScanParams {
     const float4 *X;        // row-major, row stride ld4 float4
     const float *q;         // ld floats, zero padded, device
@@ -35,6 +67,7 @@ struct ScanParams {
     uint32_t ld4;           // row stride in float4
     uint32_t k;
     uint32_t row_base;      // global id of local row 0
+    Exchange x;             // sharded mode (world > 1): fused peer exchange + global merge
 };
 
 __device__ __forceinline__ float4 ldg_stream(const float4 *p)
@@ -215,8 +248,47 @@ scan_topk_kernel(const ScanParams p)
         top.offer(key, key != 0, lane, k);
     }
     block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
+
+    bool timed_out = false;
+    if (p.x.world >= 1) {
+        // ---- fused exchange: publish the shard's top-k to every rank, wait for theirs, merge ----
+        const uint32_t world = p.x.world, slot = (uint32_t)(p.x.seq & 1);
+        uint64_t *mine = p.x.peer[p.x.rank];
+        if (warp == 0) {
+            for (uint32_t g = 0; g < world; ++g) {
+                uint64_t *dst = xchg_keys(p.x.peer[g], world, slot, p.x.rank);
+#pragma unroll
+                for (int j = 0; j < M; ++j) dst[j * 32 + lane] = (j * 32 + lane < k) ? top.v[j] : 0ull;
+            }
+            __threadfence_system();
+            __syncwarp();
+            if ((uint32_t)lane < world) st_release_sys(xchg_flag(p.x.peer[lane], world, slot, p.x.rank), p.x.seq);
+            bool ok = true;
+            if ((uint32_t)lane < world) {
+                const uint64_t *f = xchg_flag(mine, world, slot, (uint32_t)lane);
+                const long long t0 = clock64();
+                while (ld_acquire_sys(f) < p.x.seq) {
+                    if (clock64() - t0 > 4000000000ll) { ok = false; break; }   // ~2 s: a rank is missing
+                    __nanosleep(64);
+                }
+            }
+            ok = __all_sync(FULL, ok);
+            if (lane == 0) is_last = ok;   // reuse the shared flag to broadcast the outcome
+        }
+        __syncthreads();
+        timed_out = !is_last;
+        top.init();
+        const int total_x = (int)world * chunks;
+        for (int i = warp; i < total_x; i += SCAN_WARPS) {
+            const int g = i / chunks, j = i - g * chunks;
+            const uint64_t key = __ldcv(xchg_keys(mine, world, slot, (uint32_t)g) + j * 32 + lane);
+            top.offer(key, key != 0, lane, k);
+        }
+        block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
+    }
     if (warp == 0) {
         emit_results<M, METRIC>(top, k, p.out_keys, p.res_ids, p.res_scores, p.res_nfound, lane);
+        if (timed_out && p.res_nfound && lane == 0) *p.res_nfound = 0xffffffffu;   // host reports the failure
         if (lane == 0) *p.ticket = 0;
     }
 }

@@ -193,3 +193,57 @@ class GpuIndex:
         out = np.empty((n, self.dim), dtype=np.float32)
         check(self._L.sema_index_read_rows(self._h, first, n, _ptr(out)))
         return out
+
+
+class ShardGroup:
+    """Fused scan + peer exchange + merge over a row-sharded corpus (include/sema_b200.h:
+    sema_shard_group_*).  One per process / GPU; `exchange_handles` is any callable that
+    all-gathers a bytes object across the ranks and returns the list ordered by rank."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, index: GpuIndex, world: int, rank: int, exchange_handles=None):
+        self._L = _lib.lib()
+        self.index, self.world, self.rank = index, world, rank
+        self._g = C.c_void_p()
+        check(self._L.sema_shard_group_create(index.handle, world, rank, C.byref(self._g)))
+        if world > 1:
+            if exchange_handles is None:
+                raise ValueError("world > 1 needs an exchange_handles callable")
+            mine = (C.c_ubyte * self.HANDLE_BYTES)()
+            check(self._L.sema_shard_group_local_handle(self._g, mine))
+            handles = exchange_handles(bytes(mine))
+            blob = b"".join(handles)
+            if len(blob) != world * self.HANDLE_BYTES:
+                raise ValueError("handle exchange returned the wrong number of bytes")
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            check(self._L.sema_shard_group_connect(self._g, buf))
+
+    def close(self) -> None:
+        if getattr(self, "_g", None) is not None and self._g.value:
+            self._L.sema_shard_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, q: np.ndarray, k: int):
+        """Every rank calls this with the same query; every rank gets the global top-k."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        ids = np.zeros(max(k, 1), dtype=np.uint64)
+        sc = np.zeros(max(k, 1), dtype=np.float32)
+        nf = C.c_uint32()
+        check(self._L.sema_shard_group_search(self._g, _ptr(q), k, _ptr(ids), _ptr(sc), C.byref(nf)))
+        return ids[:nf.value].copy(), sc[:nf.value].copy()
+
+    def search_into(self, q: np.ndarray, k: int, ids: np.ndarray, sc: np.ndarray) -> int:
+        nf = C.c_uint32()
+        check(self._L.sema_shard_group_search(self._g, _ptr(q), k, _ptr(ids), _ptr(sc), C.byref(nf)))
+        return nf.value
+
+    def search_device(self, q_ptr: int, k: int, ids_ptr: int, scores_ptr: int, nfound_ptr: int) -> None:
+        check(self._L.sema_shard_group_search_device(self._g, C.c_void_p(q_ptr), k, C.c_void_p(ids_ptr),
+                                                     C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))

@@ -11,6 +11,21 @@ from __future__ import annotations
 import numpy as np
 
 
+def make_shard_group(index, dist):
+    """ShardGroup over torch.distributed: the 64-byte IPC handles travel by all_gather_object."""
+    from .index import ShardGroup
+    world, rank = dist.get_world_size(), dist.get_rank()
+
+    def exchange(mine: bytes):
+        out = [None] * world
+        dist.all_gather_object(out, mine)
+        return out
+
+    g = ShardGroup(index, world, rank, exchange)
+    dist.barrier()
+    return g
+
+
 def shard_range(n_rows: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous row range [lo, hi) of shard `rank` (ceil split; trailing shards may be short or empty)."""
     per = (n_rows + world - 1) // world

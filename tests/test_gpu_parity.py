@@ -476,3 +476,27 @@ def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
     r = oracle_c.scan_batch(X, Q, 10)
     for i in range(9):
         O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+
+
+# ---------------------------------------------------------------- fused shard exchange
+def test_shard_group_world1_equals_plain_search(sema, oracle_c):
+    # the fused publish / wait / merge path with a single rank (real multi-rank runs: bench.py --gpus N)
+    n, d, k = 40000, 384, 10
+    X = _unit(1, n, d)
+    Q = _unit(2, 5, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.set_row_base(7_000_000)
+        idx.append(X, normalize=False)
+        g = sema.ShardGroup(idx, 1, 0)
+        try:
+            for q in Q:
+                ids, sc = g.search(q, k)
+                r_ids, r_sc = oracle_c.scan(X, q, k, id_base=7_000_000)
+                O.check_parity(ids, sc, r_ids, r_sc)
+                ids100, sc100 = g.search(q, 100)
+                r_ids, r_sc = oracle_c.scan(X, q, 100, id_base=7_000_000)
+                O.check_parity(ids100, sc100, r_ids, r_sc)
+            with pytest.raises(sema.SemaError):
+                g.search(Q[0], 200)                      # the fused exchange covers k <= 128
+        finally:
+            g.close()
