@@ -192,6 +192,8 @@ scan_topk_kernel(const ScanParams p)
     const int my_r = row_of_lane<R>(lane);
     const bool rep = (lane & (32 / R - 1)) == 0;
 
+    // static stride over batches (a dynamic chunk scheduler was measured and gave nothing: the
+    // kernel is limited by the memory system, not by SM-to-SM imbalance)
     for (uint32_t b = gw; b < nb; b += nw) {
         const uint32_t row0 = b * R;
         float acc[R];
@@ -239,13 +241,25 @@ scan_topk_kernel(const ScanParams p)
     if (!is_last) return;
     __threadfence();
 
+    // Only the first k entries of each block list matter.  They are read as one flat array of
+    // gridDim.x * k keys, U independent loads per lane in flight: this merge sits on the critical
+    // path after the last block arrives, so its load latency must overlap, not add up.
     top.init();
     const int chunks = (k + 31) >> 5;
-    const int total = (int)gridDim.x * chunks;
-    for (int i = warp; i < total; i += SCAN_WARPS) {
-        const int bb = i / chunks, j = i - bb * chunks;
-        const uint64_t key = __ldcg(p.partials + (size_t)bb * 32 * M + j * 32 + lane);
-        top.offer(key, key != 0, lane, k);
+    {
+        constexpr int U = 8;
+        const int totalk = (int)gridDim.x * k;
+        for (int base = warp * 32; base < totalk; base += SCAN_WARPS * 32 * U) {
+            uint64_t kk[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * SCAN_WARPS * 32 + lane;
+                const int bb = idx / k, e = idx - bb * k;
+                kk[u] = idx < totalk ? __ldcg(p.partials + (size_t)bb * 32 * M + e) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) top.offer(kk[u], kk[u] != 0, lane, k);
+        }
     }
     block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
 

@@ -182,9 +182,9 @@ int scan_shape(sema_index *s, const ScanArgs &a)
     const uint32_t ld4 = s->ld / 4;
     if (ld4 == 96) {
         switch (s->variant) {
-            case 1: return scan_m<3, 8, METRIC>(s, a);
+            case 1: return scan_m<3, 4, METRIC>(s, a);
             case 2: return scan_m<3, 2, METRIC>(s, a);
-            default: return scan_m<3, 4, METRIC>(s, a);
+            default: return scan_m<3, 8, METRIC>(s, a);   // R = 8: best or tied on every box measured
         }
     }
     if (ld4 == 192) {
@@ -622,8 +622,8 @@ int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metr
     CKD(cudaHostAlloc(&s->q_pin, s->ld * sizeof(float), cudaHostAllocPortable));
     memset(s->q_pin, 0, s->ld * sizeof(float));
     CKD(cudaMalloc(&s->partials, (size_t)s->num_sms * MAX_BLOCKS_PER_SM * K_PASS * sizeof(uint64_t)));
-    CKD(cudaMalloc(&s->ticket, sizeof(unsigned int)));
-    CKD(cudaMemset(s->ticket, 0, sizeof(unsigned int)));
+    CKD(cudaMalloc(&s->ticket, 2 * sizeof(unsigned int)));
+    CKD(cudaMemset(s->ticket, 0, 2 * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
     CKD(cudaMalloc(&s->max_norm2, sizeof(float)));
     CKD(cudaMalloc(&s->qscratch, 65536 + 16));
