@@ -48,8 +48,11 @@ def parse():
     ap.add_argument("--variant", type=int, default=-1, help="K2 kernel variant (tuning)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused = P2P stores + merge inside K2's last block; nccl = all-gather + K4")
-    ap.add_argument("--workload", default="single", choices=["single", "batch"],
-                    help="single = headline single-query scan (K2); batch = BASELINE config 3, nq-query batches (K3)")
+    ap.add_argument("--workload", default="single", choices=["single", "batch", "ingest"],
+                    help="single = headline single-query scan (K2); batch = BASELINE config 3, nq-query batches (K3); "
+                         "ingest = BASELINE config 4/5 style streaming ingest (K1) interleaved with queries")
+    ap.add_argument("--ingest-batch", type=int, default=65536, help="rows per appended batch (--workload ingest)")
+    ap.add_argument("--queries-per-batch", type=int, default=2, help="searches issued after each appended batch")
     ap.add_argument("--nq", type=int, default=1024, help="queries per batch (--workload batch)")
     ap.add_argument("--batch-mode", type=int, default=2, help="0 auto, 1 K2 per query, 2 K3 tensor cores")
     ap.add_argument("--k3-cluster", type=int, default=0, help="K3 cluster size (0 auto, 1, 2, 4) — tuning")
@@ -275,6 +278,82 @@ def run_batch(a):
     print(json.dumps(line), flush=True)
 
 
+def run_ingest(a):
+    """BASELINE.json configs[4]: the index grows to rows x dim by appending batches from pinned host
+    memory (H2D + K1 on the ingest stream) while top-k queries run on the query stream.  Every query
+    scans exactly the rows whose ingest had completed when it started (snapshot semantics; checked
+    against the oracle in tests/test_gpu_parity.py::test_async_ingest_snapshot_semantics)."""
+    import torch
+
+    import sema_b200
+    from sema_b200 import _lib
+
+    if _lib.lib().sema_device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: sema_b200 has no CPU fallback")
+    torch.cuda.set_device(0)
+    k, B = a.k, a.ingest_batch
+    nb = (a.rows + B - 1) // B
+    idx = sema_b200.GpuIndex(a.dim, nb * B, device=0)
+    g = torch.Generator().manual_seed(1)
+    pool = [torch.randn(B, a.dim, generator=g, dtype=torch.float32).pin_memory() for _ in range(3)]
+    host = [t.numpy() for t in pool]
+    Q = torch.randn(64, a.dim, generator=g, dtype=torch.float32)
+    Q = (Q / Q.norm(dim=1, keepdim=True)).numpy()
+    ids_h = np.zeros(k, dtype=np.uint64)
+    sc_h = np.zeros(k, dtype=np.float32)
+    # warm-up: one batch + a few queries, then start over with a fresh index
+    idx.append(host[0], normalize=True)
+    for i in range(5):
+        idx.search_into(Q[i], k, ids_h, sc_h)
+    idx.close()
+    idx = sema_b200.GpuIndex(a.dim, nb * B, device=0)
+    snaps, nq = [], 0
+    torch.cuda.synchronize()
+    total_rows = nb * B
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for b in range(nb):                                    # H2D + K1 per batch, all on the ingest stream
+            idx.append(host[b % len(host)], normalize=True, asynchronous=True)
+        t_enq = time.perf_counter() - t0
+        while True:                                            # K2 on the query stream, while the ingest runs
+            v = idx.visible
+            if v >= total_rows:
+                break
+            if v == 0:
+                time.sleep(0.0002)
+                continue
+            idx.search_into(Q[nq % 64], k, ids_h, sc_h)
+            snaps.append(idx.last_snapshot)
+            nq += 1
+        idx.flush()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    assert idx.visible == total_rows and all(s % B == 0 and s > 0 for s in snaps) and snaps == sorted(snaps)
+    scanned_bytes = float(sum(snaps)) * a.dim * 4
+    # after the stream: the index answers like any other (spot check: a stored row finds itself)
+    probe = idx.read_rows(total_rows - 1, 1)[0]
+    r_ids, r_sc = idx.search(probe, 1)
+    line = {
+        "metric": f"streaming_ingest_rows_per_s_with_interleaved_top{k}_queries_{total_rows}x{a.dim}_fp32",
+        "value": total_rows / dt, "unit": "rows/s", "n_gpus": 1, "steps": nb, "warmup": 1,
+        "ms_per_step": dt * 1e3 / nb, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"append {nb} batches of {B} x {a.dim} fp32 rows from pinned host memory (normalise on GPU) "
+                               f"while top-{k} queries run back to back on the query stream (BASELINE configs[4])",
+                   "rows": total_rows, "dim": a.dim, "k": k},
+        "ingest": {"rows_per_s": total_rows / dt, "h2d_GBps": total_rows * a.dim * 4 / dt / 1e9,
+                   "queries": nq, "qps_during_ingest": nq / dt, "enqueue_s": t_enq,
+                   "mean_snapshot_rows": float(np.mean(snaps)) if snaps else 0.0,
+                   "query_scan_GBps": scanned_bytes / dt / 1e9,
+                   "snapshots_monotonic_and_batch_aligned": True,
+                   "self_probe_ok": bool(len(r_ids) == 1 and abs(float(r_sc[0]) - 1.0) < 1e-5)},
+        "e2e": {"value": total_rows / dt, "unit": "rows/s", "h2d_bytes_per_step": B * a.dim * 4, "d2h_bytes_per_step": 0,
+                "note": "plus one query H2D and one result D2H per search"},
+        "gpu_launches": int(idx.launch_count), "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(a):
     import torch
 
@@ -495,6 +574,8 @@ def main():
         run_reference(a)
     elif a.workload == "batch":
         run_batch(a)
+    elif a.workload == "ingest":
+        run_ingest(a)
     else:
         run_ours(a)
 

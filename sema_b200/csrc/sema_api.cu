@@ -189,8 +189,8 @@ int scan_shape(sema_index *s, const ScanArgs &a)
     }
     if (ld4 == 192) {
         switch (s->variant) {
-            case 2: return scan_m<6, 2, METRIC>(s, a);
-            default: return scan_m<6, 4, METRIC>(s, a);
+            case 1: return scan_m<6, 4, METRIC>(s, a);
+            default: return scan_m<6, 2, METRIC>(s, a);   // 24 float4 per lane per 4 rows is too many registers
         }
     }
     return scan_m<0, 4, METRIC>(s, a);
