@@ -102,8 +102,12 @@ int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32
 /* Same with queries and results resident on the device (Q_dev: nq x dim dense). */
 int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
-/* mode 0 = automatic, 1 = always K2 per query, 2 = K3 whenever the shape allows; other values
- * only query.  Returns the mode now active. */
+/* mode 0 = automatic (K3 with the bf16x3 split when the shape allows and nq >= 4), 1 = always K2
+ * per query, 2 = K3 bf16x3 whenever the shape allows, 3 = K3 with a single bf16 pass as a coarser
+ * candidate filter (a third of the tensor work; the exact fp32 re-scoring and the per-query
+ * exactness proof are unchanged, so results are still identical — queries whose proof fails under
+ * the looser 1-pass error bound are re-run through K2); other values only query.  Returns the
+ * mode now active. */
 int sema_index_set_batch_mode(sema_index *idx, int mode);
 /* queries served by K3 so far, and how many of them were re-run through K2 because exactness
  * could not be proven from the candidate lists (heavy ties / duplicates). */

@@ -248,28 +248,34 @@ struct Params {
     uint32_t dim;
 };
 
-template <int KC>
+// PASSES = 3: bf16x3 split (hi.hi + lo.hi + hi.lo), a stage holds the hi and lo plane blocks.
+// PASSES = 1: single bf16 pass as a coarser candidate filter (only the hi plane block is fetched;
+//             the exactness proof then uses the 1-pass error bound and falls back more readily).
+template <int KC, int PASSES>
 struct Smem {
+    static constexpr int STAGE = PASSES == 3 ? STAGE_BYTES : STAGE_PLANE_BYTES;
     static constexpr int LIST_BYTES = KC * TILE_Q * 8;     // scores f32 + rows u32
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int STAGES = (227 * 1024 - LIST_BYTES - BAR_BYTES) / STAGE_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + LIST_BYTES + BAR_BYTES;
+    static constexpr int STAGES_RAW = (227 * 1024 - LIST_BYTES - BAR_BYTES) / STAGE;
+    static constexpr int STAGES = STAGES_RAW > 24 ? 24 : STAGES_RAW;
+    static constexpr int TOTAL = STAGES * STAGE + LIST_BYTES + BAR_BYTES;
 };
 
 // C = CTAs per cluster.  The C CTAs of a cluster hold C different query tiles and stream the
 // same corpus tiles: every stage is fetched once per cluster (each CTA issues 1/C of it) and
 // multicast into all C shared memories, cutting the L2->SM operand traffic C-fold.
-template <int KC, int C>
+template <int KC, int C, int PASSES>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_kernel(const Params p)
 {
-    using S = Smem<KC>;
+    using S = Smem<KC, PASSES>;
     constexpr int STAGES = S::STAGES;
+    constexpr int STAGE = S::STAGE;          // bytes fetched per k-block
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem;
-    float *list_sc = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);        // [KC][128]
+    float *list_sc = reinterpret_cast<float *>(smem + STAGES * STAGE);              // [KC][128]
     uint32_t *list_row = reinterpret_cast<uint32_t *>(list_sc + KC * TILE_Q);       // [KC][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + S::LIST_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE + S::LIST_BYTES);
     uint64_t *full = bars;                    // [STAGES]  TMA -> MMA
     uint64_t *empty = bars + STAGES;          // [STAGES]  MMA -> TMA
     uint64_t *acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -305,7 +311,7 @@ batch_scan_kernel(const Params p)
     const uint32_t acc_col = 2 * acols;      // accumulators follow the two query planes
     const uint32_t crank = C > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t cmask = (uint16_t)((1u << C) - 1u);
-    constexpr uint32_t SLICE = STAGE_BYTES / C;
+    constexpr uint32_t SLICE = STAGE / C;
 
     // ---- epilogue warps stage the query tile into TMEM (A operand): row m <-> lane m
     if (warp >= 2) {
@@ -327,7 +333,7 @@ batch_scan_kernel(const Params p)
                 lo[e] = pack_bf16(v[2 * e] - bf16_round(v[2 * e]), v[2 * e + 1] - bf16_round(v[2 * e + 1]));
             }
             tmem_st8(lane_addr + c / 2, hi);
-            tmem_st8(lane_addr + acols + c / 2, lo);
+            if (PASSES == 3) tmem_st8(lane_addr + acols + c / 2, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -344,11 +350,12 @@ batch_scan_kernel(const Params p)
                 const unsigned char *src = p.planes + (size_t)t * tile_bytes((int)p.dim);
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);     // all C consumers released this stage
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], STAGE);
+                    // the planes hold [hi | lo] per k-block; a 1-pass stage fetches the hi half only
                     if (C == 1)
-                        bulk_g2s(ring + stage * STAGE_BYTES, src + (size_t)kb * STAGE_BYTES, STAGE_BYTES, &full[stage]);
+                        bulk_g2s(ring + stage * STAGE, src + (size_t)kb * STAGE_BYTES, STAGE, &full[stage]);
                     else
-                        bulk_g2s_multicast(ring + stage * STAGE_BYTES + crank * SLICE,
+                        bulk_g2s_multicast(ring + stage * STAGE + crank * SLICE,
                                            src + (size_t)kb * STAGE_BYTES + crank * SLICE, SLICE, &full[stage], cmask);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -370,7 +377,7 @@ batch_scan_kernel(const Params p)
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t sb = smem_u32(ring + stage * STAGE_BYTES);
+                    const uint32_t sb = smem_u32(ring + stage * STAGE);
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
                         const uint32_t a_hi = tmem + kb * (BLOCK_K / 2) + j * (UMMA_K / 2);
@@ -378,8 +385,10 @@ batch_scan_kernel(const Params p)
                         const uint64_t b_hi = make_b_desc(sb + j * 2 * (TILE_N * 16), TILE_N * 16, 128);
                         const uint64_t b_lo = make_b_desc(sb + STAGE_PLANE_BYTES + j * 2 * (TILE_N * 16), TILE_N * 16, 128);
                         umma_ts(d_tmem, a_hi, b_hi, idesc, (kb | j) != 0);
-                        umma_ts(d_tmem, a_lo, b_hi, idesc, 1);
-                        umma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                        if (PASSES == 3) {
+                            umma_ts(d_tmem, a_lo, b_hi, idesc, 1);
+                            umma_ts(d_tmem, a_hi, b_lo, idesc, 1);
+                        }
                     }
                     if (C == 1) umma_commit(&empty[stage]);   // frees the smem stage when the MMAs retire
                     else umma_commit_multicast(&empty[stage], cmask);   // ... in every CTA of the cluster

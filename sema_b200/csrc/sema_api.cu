@@ -93,7 +93,7 @@ struct sema_index {
     float *cand_thr = nullptr;
     uint32_t *flags_dev = nullptr, *flags_pin = nullptr;
     size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
-    int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 whenever the shape allows
+    int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 bf16x3 whenever the shape allows, 3 K3 single bf16 pass
     int k3_cluster = 0;                 // 0 auto, else forced cluster size (1, 2, 4) — tuning
     int normalize_queries = 0;          // apply K1 to host queries before scanning
     unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch]
@@ -295,6 +295,7 @@ int publish(sema_index *s, uint64_t n)
 // ---- K3 dispatch -----------------------------------------------------------------
 constexpr uint32_t K3_MAX_K = 100;
 constexpr float K3_ERR_REL = 2.5e-4f;  // >= 3*2^-16 (dropped split terms) + fp32 accumulation over 3*dim terms
+constexpr float K3_ERR_REL_1PASS = 8.5e-3f;  // >= 2*2^-8 + 2^-16 (both operands rounded to bf16) + accumulation
 
 bool k3_shape_ok(const sema_index *s, uint32_t k)
 {
@@ -329,19 +330,19 @@ int k3_sync_planes(sema_index *s, uint64_t n)
     return SEMA_OK;
 }
 
-template <int KC, int C>
+template <int KC, int C, int PASSES>
 int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_tiles)
 {
-    auto kern = k3::batch_scan_kernel<KC, C>;
+    auto kern = k3::batch_scan_kernel<KC, C, PASSES>;
     static bool attr_set[64] = {false};
     if (!attr_set[s->device & 63]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC>::TOTAL));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC, PASSES>::TOTAL));
         attr_set[s->device & 63] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(q_tiles, p.parts, 1);
     cfg.blockDim = dim3(k3::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = k3::Smem<KC>::TOTAL;
+    cfg.dynamicSmemBytes = k3::Smem<KC, PASSES>::TOTAL;
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -362,15 +363,15 @@ int k3_max_clusters(sema_index *s, int *out)
     static int cached[64] = {0};
     int &v = cached[s->device & 63];
     if (v == 0) {
-        auto kern = k3::batch_scan_kernel<KC, C>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC>::TOTAL));
+        auto kern = k3::batch_scan_kernel<KC, C, 3>;   // the 1-pass kernel uses no more shared memory
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC, 3>::TOTAL));
         if (C == 1) {
             v = s->num_sms;
         } else {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(C, (unsigned)s->num_sms, 1);
             cfg.blockDim = dim3(k3::THREADS, 1, 1);
-            cfg.dynamicSmemBytes = k3::Smem<KC>::TOTAL;
+            cfg.dynamicSmemBytes = k3::Smem<KC, 3>::TOTAL;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = C;
@@ -387,11 +388,16 @@ int k3_max_clusters(sema_index *s, int *out)
     return SEMA_OK;
 }
 
-template <int KC>
-int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_tiles, int c)
+template <int KC, int PASSES>
+int k3_launch_scan_p(sema_index *s, const k3::Params &p, uint32_t q_tiles, int c)
 {
-    return c == 4 ? k3_launch_scan_c<KC, 4>(s, p, q_tiles)
-         : c == 2 ? k3_launch_scan_c<KC, 2>(s, p, q_tiles) : k3_launch_scan_c<KC, 1>(s, p, q_tiles);
+    return c == 4 ? k3_launch_scan_c<KC, 4, PASSES>(s, p, q_tiles)
+         : c == 2 ? k3_launch_scan_c<KC, 2, PASSES>(s, p, q_tiles) : k3_launch_scan_c<KC, 1, PASSES>(s, p, q_tiles);
+}
+template <int KC>
+int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_tiles, int c, int passes)
+{
+    return passes == 1 ? k3_launch_scan_p<KC, 1>(s, p, q_tiles, c) : k3_launch_scan_p<KC, 3>(s, p, q_tiles, c);
 }
 template <int KC>
 int k3_clusters(sema_index *s, int c, int *out)
@@ -404,6 +410,7 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
              uint32_t *nf_d)
 {
     const uint32_t kc = k <= 16 ? 32 : (k <= 48 ? 64 : 128);
+    const int passes = s->batch_mode == 3 ? 1 : 3;
     const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
     const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
     int rc;
@@ -422,7 +429,10 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
 
     // Cluster size C: C query tiles share one stream of corpus tiles (TMA multicast).  The
     // query-tile count is padded to a multiple of C (Qpad rows beyond nq are zero queries).
-    const int csize = s->k3_cluster > 0 ? s->k3_cluster : (q_tiles_all >= 4 ? 4 : (q_tiles_all >= 2 ? 2 : 1));
+    // measured on 10M x 384 x 1024q: bf16x3 is fastest with clusters of 4 (128 SMs, higher clocks under the
+    // power cap), the single-pass filter with clusters of 2 (144 SMs; it is bound by L2->SM delivery)
+    const int cpref = passes == 1 ? 2 : 4;
+    const int csize = s->k3_cluster > 0 ? s->k3_cluster : (q_tiles_all >= (uint32_t)cpref ? cpref : (q_tiles_all >= 2 ? 2 : 1));
     int max_clusters = 1;
     rc = kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
     if (rc) return rc;
@@ -450,7 +460,7 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         p.n_tiles = n_tiles;
         p.parts = parts;
         p.dim = s->dim;
-        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_tiles, csize) : kc == 64 ? k3_launch_scan<64>(s, p, q_tiles, csize) : k3_launch_scan<128>(s, p, q_tiles, csize);
+        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_tiles, csize, passes) : kc == 64 ? k3_launch_scan<64>(s, p, q_tiles, csize, passes) : k3_launch_scan<128>(s, p, q_tiles, csize, passes);
         if (rc) return rc;
         const uint32_t q_first = qt0 * k3::TILE_Q;
         if (q_first >= nq) break;
@@ -471,7 +481,7 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         r.kc = kc;
         r.row_base = s->row_base;
         r.max_norm2 = s->max_norm2;
-        r.err_rel = K3_ERR_REL;
+        r.err_rel = passes == 1 ? K3_ERR_REL_1PASS : K3_ERR_REL;
         if (k <= 32) k3::rescore_kernel<1><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
         else if (k <= 64) k3::rescore_kernel<2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
         else k3::rescore_kernel<4><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
@@ -495,7 +505,7 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
 int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
                uint32_t *nf_d)
 {
-    const bool want_k3 = s->batch_mode == 2 || (s->batch_mode == 0 && nq >= 4);
+    const bool want_k3 = s->batch_mode >= 2 || (s->batch_mode == 0 && nq >= 4);
     if (want_k3 && k3_shape_ok(s, k)) {
         int rc = k3_sync_planes(s, n);
         if (rc == SEMA_OK) return k3_batch(s, Qd, nq, n, k, ids_d, sc_d, nf_d);
@@ -861,7 +871,7 @@ int sema_index_set_normalize_queries(sema_index *s, int on)
 int sema_index_set_batch_mode(sema_index *s, int mode)
 {
     if (!s) return -1;
-    if (mode >= 0 && mode <= 2) s->batch_mode = mode;
+    if (mode >= 0 && mode <= 3) s->batch_mode = mode;
     return s->batch_mode;
 }
 

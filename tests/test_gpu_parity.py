@@ -381,14 +381,15 @@ K3_CASES = [
 ]
 
 
+@pytest.mark.parametrize("mode", [2, 3], ids=["bf16x3", "bf16x1"])
 @pytest.mark.parametrize("n,nq,k", K3_CASES)
-def test_k3_batch_matches_oracle_and_k2(sema, oracle_c, n, nq, k):
+def test_k3_batch_matches_oracle_and_k2(sema, oracle_c, n, nq, k, mode):
     d = 384
     X = _unit(1, n, d)
     Q = _unit(2, nq, d)
     with sema.GpuIndex(d, n) as idx:
         idx.append(X, normalize=False)
-        assert idx.set_batch_mode(2) == 2                 # tensor-core path
+        assert idx.set_batch_mode(mode) == mode           # tensor-core path (3 passes / 1 pass)
         ids3, sc3, nf3 = idx.search_batch(Q, k)
         served, fallbacks = idx.batch_stats()
         assert served == nq                                # K3 really ran
@@ -416,6 +417,9 @@ def test_k3_ties_and_duplicates_fall_back_to_exact_path(sema, oracle_c):
         idx.set_batch_mode(2)
         ids, sc, nf = idx.search_batch(Q, k)
         served, fallbacks = idx.batch_stats()
+        idx.set_batch_mode(3)                             # the single-pass filter must stay exact too
+        ids1, sc1, nf1 = idx.search_batch(Q, k)
+    assert np.array_equal(ids, ids1) and np.array_equal(sc, sc1)
     assert served == 8 and fallbacks >= 1
     assert ids[0].tolist() == [123] + list(range(5000, 5009))
     r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
