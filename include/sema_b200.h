@@ -83,6 +83,22 @@ int sema_index_append_synthetic(sema_index *idx, uint64_t seed, uint64_t synth_r
  * (src/storage/lance_indexer.rs:234-250): the listed local rows stop matching. */
 int sema_index_tombstone(sema_index *idx, const uint64_t *rows, uint64_t n);
 
+/* Compaction after deletions (LanceDB's `optimize`/compact step for the delete at
+ * src/storage/lance_indexer.rs:234-250): live rows move down, keeping their order, dead rows
+ * (null / tombstoned) disappear and size shrinks.  new_row_of_old (may be NULL) receives, for every
+ * old row, its new index or UINT64_MAX if it was dropped, so the caller can remap its row -> Chunk
+ * table; *n_live (may be NULL) the new size. */
+int sema_index_compact(sema_index *idx, uint64_t *new_row_of_old, uint64_t *n_live);
+/* Same with an explicit keep mask (one byte per row, 0 = drop): kept rows keep their state, so a
+ * null-vector row that is kept stays a (never matching) null row. */
+int sema_index_compact_keep(sema_index *idx, const uint8_t *keep, uint64_t *new_row_of_old, uint64_t *n_live);
+
+/* On-disk cache of the vector column: the raw rows x dim fp32 matrix as stored
+ * (already normalised) plus the validity bytes, so a restart re-uploads instead of re-embedding.
+ * File: 64-byte header {"SEMAIDX1", dim, metric, n_rows}, n_rows validity bytes, n_rows*dim floats. */
+int sema_index_save(sema_index *idx, const char *path);
+int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_index **out);
+
 /* ---- search (kernel K2; K3 for batches) -----------------------------------
  * Replaces table.query().nearest_to(q)?.limit(k).execute()
  * (src/storage/lance_indexer.rs:121-126).  q: dim floats (unit-norm for cosine).

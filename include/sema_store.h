@@ -93,6 +93,10 @@ int sema_store_group_results_by_file(sema_store *st, const sema_hit *hits, uint3
  * file_path equals `file_path` stops matching.  *removed (may be NULL) = rows deleted. */
 int sema_store_remove_file_chunks(sema_store *st, const char *file_path, uint64_t *removed);
 
+/* Compaction after deletions: chunks removed by sema_store_remove_file_chunks leave both the GPU
+ * matrix and the row -> Chunk table; rows are renumbered (order kept).  *n_live (may be NULL). */
+int sema_store_compact(sema_store *st, uint64_t *n_live);
+
 /* extract_chunk_from_batch (src/storage/lance_indexer.rs:252-281): the Chunk of a row.  The
  * returned strings belong to the store and stay valid until it is destroyed. */
 int sema_store_chunk(const sema_store *st, uint64_t row, const char **id, const char **file_path,

@@ -40,6 +40,10 @@ SIGNATURES = {
     "sema_index_append_device": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_int, _u64p]),
     "sema_index_append_synthetic": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _u64p]),
     "sema_index_tombstone": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "sema_index_compact": (C.c_int, [_vp, _vp, _u64p]),
+    "sema_index_compact_keep": (C.c_int, [_vp, _vp, _vp, _u64p]),
+    "sema_index_save": (C.c_int, [_vp, C.c_char_p]),
+    "sema_index_load": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_vp)]),
     "sema_index_search": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _u32p]),
     "sema_index_search_batch": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_index_search_batch_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),

@@ -190,6 +190,27 @@ Status GpuVectorIndexer::remove_file_chunks(const std::string &file_path, uint64
     return Status::Ok();
 }
 
+Status GpuVectorIndexer::compact(uint64_t *n_live)
+{
+    if (n_live) *n_live = chunks_.size();
+    if (!idx_ || chunks_.empty()) return Status::Ok();
+    std::vector<uint64_t> map(chunks_.size());
+    uint64_t live = 0;
+    // keep every chunk that was not removed — also those whose embedding failed: they never match a
+    // vector query but the reference's LIKE fallback still finds them
+    int rc = sema_index_compact_keep(idx_, live_.data(), map.data(), &live);
+    if (rc) return from_rc(rc);
+    std::vector<Chunk> kept;
+    kept.reserve(live);
+    for (uint64_t r = 0; r < chunks_.size(); ++r)
+        if (map[r] != ~0ull) kept.push_back(std::move(chunks_[r]));   // the map is order preserving
+    if (kept.size() != live) return Status::Err(SEMA_ERR_INVALID, "compaction map out of step with the chunk table");
+    chunks_ = std::move(kept);
+    live_.assign(chunks_.size(), 1);
+    if (n_live) *n_live = live;
+    return Status::Ok();
+}
+
 // ------------------------------------------------------------------ StorageManager
 Status StorageManager::search(const std::string &query_in, size_t limit, std::vector<std::pair<Chunk, float>> *out,
                               std::vector<uint64_t> *rows)
@@ -412,6 +433,13 @@ int sema_store_remove_file_chunks(sema_store *st, const char *file_path, uint64_
 {
     if (!st || !file_path) return store_fail(SEMA_ERR_INVALID, "null argument");
     Status s = st->mgr.lance_indexer.remove_file_chunks(file_path, removed);
+    return s.ok() ? SEMA_OK : store_fail(s);
+}
+
+int sema_store_compact(sema_store *st, uint64_t *n_live)
+{
+    if (!st) return store_fail(SEMA_ERR_INVALID, "null store");
+    Status s = st->mgr.lance_indexer.compact(n_live);
     return s.ok() ? SEMA_OK : store_fail(s);
 }
 

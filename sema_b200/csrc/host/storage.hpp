@@ -87,6 +87,10 @@ public:
     // remove_file_chunks (:234-250)
     Status remove_file_chunks(const std::string &file_path, uint64_t *removed = nullptr);
 
+    // compaction after deletions: drops removed rows on the GPU and renumbers the row -> Chunk
+    // table to match (row ids returned by later searches refer to the compacted table)
+    Status compact(uint64_t *n_live = nullptr);
+
     const Chunk *chunk(uint64_t row) const { return row < chunks_.size() ? &chunks_[row] : nullptr; }
     uint64_t len() const { return chunks_.size(); }
     uint32_t dim() const { return dim_; }

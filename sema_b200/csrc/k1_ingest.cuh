@@ -124,4 +124,18 @@ tombstone_kernel(float *X, uint32_t ld, const uint64_t *rows, uint64_t n, uint64
     }
 }
 
+// compaction: dst[i] = X[src[i]] for i in [0, m) — one warp per row, float4 granularity
+__global__ void __launch_bounds__(INGEST_THREADS)
+gather_rows_kernel(const float *X, uint32_t ld, const uint32_t *src, uint64_t m, float *dst)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp0; i < m; i += nwarps) {
+        const float4 *s = reinterpret_cast<const float4 *>(X + (uint64_t)src[i] * ld);
+        float4 *d = reinterpret_cast<float4 *>(dst + i * ld);
+        for (uint32_t j = lane; j < ld / 4; j += 32) d[j] = s[j];
+    }
+}
+
 }  // namespace sema

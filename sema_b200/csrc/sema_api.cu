@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <deque>
+#include <vector>
 #include <mutex>
 #include <new>
 
@@ -770,6 +771,156 @@ int sema_index_tombstone(sema_index *s, const uint64_t *rows, uint64_t n)
     uint64_t lowest = s->planes_rows;
     for (uint64_t i = 0; i < n; ++i) if (rows[i] < lowest) lowest = rows[i];
     s->planes_rows = lowest;
+    return SEMA_OK;
+}
+
+
+int sema_index_compact(sema_index *s, uint64_t *new_row_of_old, uint64_t *n_live_out)
+{
+    return sema_index_compact_keep(s, nullptr, new_row_of_old, n_live_out);
+}
+
+int sema_index_compact_keep(sema_index *s, const uint8_t *keep, uint64_t *new_row_of_old, uint64_t *n_live_out)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    const uint64_t n = s->n_rows;
+    std::vector<uint8_t> valid(n ? n : 1);
+    if (n) CK(cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> src;   // src[new] = old, ascending
+    std::vector<uint8_t> new_valid;
+    src.reserve(n);
+    new_valid.reserve(n);
+    for (uint64_t r = 0; r < n; ++r) {
+        if (keep ? keep[r] != 0 : valid[r] != 0) {
+            new_valid.push_back(valid[r]);
+            if (new_row_of_old) new_row_of_old[r] = src.size();
+            src.push_back((uint32_t)r);
+        } else if (new_row_of_old) {
+            new_row_of_old[r] = ~0ull;
+        }
+    }
+    const uint64_t live = src.size();
+    if (n_live_out) *n_live_out = live;
+    if (live == n) return SEMA_OK;  // nothing to drop
+    // gather through a bounce buffer, chunk by chunk in ascending order: a chunk's destination
+    // [j*C, (j+1)*C) never overlaps a later chunk's sources (src[i] >= i)
+    const uint64_t C = 1u << 16;
+    float *tmp = nullptr;
+    uint32_t *src_dev = nullptr;
+    cudaError_t e = cudaMalloc(&tmp, C * s->ld * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&src_dev, C * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        cudaFree(tmp); cudaFree(src_dev); cudaGetLastError();
+        return fail(SEMA_ERR_NOMEM, "compaction scratch: %s", cudaGetErrorString(e));
+    }
+    uint64_t first_moved = 0;
+    while (first_moved < live && src[first_moved] == first_moved) ++first_moved;   // untouched prefix
+    for (uint64_t at = first_moved; at < live; at += C) {
+        const uint64_t m = (live - at) < C ? (live - at) : C;
+        CK(cudaMemcpyAsync(src_dev, src.data() + at, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        uint64_t blocks = (m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+        if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
+        gather_rows_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, src_dev, m, tmp);
+        CK(cudaGetLastError());
+        s->launches++;
+        CK(cudaMemcpyAsync(s->X + at * s->ld, tmp, m * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));   // src_dev / tmp are reused by the next chunk
+    }
+    if (live) CK(cudaMemcpyAsync(s->valid, new_valid.data(), live, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(tmp);
+    cudaFree(src_dev);
+    s->n_rows = live;
+    s->n_visible = live;
+    if (s->planes_rows > first_moved) s->planes_rows = first_moved;   // K3 planes: re-tile from the first moved row
+    return SEMA_OK;
+}
+
+namespace {
+struct SemaFileHeader {
+    char magic[8];
+    uint32_t dim;
+    int32_t metric;
+    uint64_t n_rows;
+    unsigned char pad[40];
+};
+static_assert(sizeof(SemaFileHeader) == 64, "header is 64 bytes");
+}  // namespace
+
+int sema_index_save(sema_index *s, const char *path)
+{
+    if (!s || !path) return fail(SEMA_ERR_INVALID, "null argument");
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(SEMA_ERR_INVALID, "cannot open %s for writing", path);
+    SemaFileHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "SEMAIDX1", 8);
+    h.dim = s->dim;
+    h.metric = s->metric;
+    h.n_rows = s->n_rows;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    const uint64_t n = s->n_rows;
+    std::vector<uint8_t> valid(n ? n : 1);
+    if (ok && n) {
+        cudaError_t e = cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost);
+        ok = e == cudaSuccess && fwrite(valid.data(), 1, n, f) == n;
+    }
+    const uint64_t C = 1u << 16;
+    float *pin = nullptr;
+    if (ok && n) ok = cudaHostAlloc(&pin, C * s->dim * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+    for (uint64_t at = 0; ok && at < n; at += C) {
+        const uint64_t m = (n - at) < C ? (n - at) : C;
+        cudaError_t e = cudaMemcpy2D(pin, s->dim * sizeof(float), s->X + at * s->ld, s->ld * sizeof(float),
+                                     s->dim * sizeof(float), m, cudaMemcpyDeviceToHost);
+        ok = e == cudaSuccess && fwrite(pin, sizeof(float), m * s->dim, f) == m * s->dim;
+    }
+    if (pin) cudaFreeHost(pin);
+    ok = (fclose(f) == 0) && ok;
+    cudaGetLastError();
+    return ok ? SEMA_OK : fail(SEMA_ERR_CUDA, "writing %s failed", path);
+}
+
+int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_index **out)
+{
+    if (!path || !out) return fail(SEMA_ERR_INVALID, "null argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(SEMA_ERR_INVALID, "cannot open %s", path);
+    SemaFileHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SEMAIDX1", 8) != 0) {
+        fclose(f);
+        return fail(SEMA_ERR_INVALID, "%s is not a sema index file", path);
+    }
+    if (capacity_rows < h.n_rows) capacity_rows = h.n_rows;
+    sema_index *s = nullptr;
+    int rc = sema_index_create(device, h.dim, capacity_rows, h.metric, &s);
+    if (rc) { fclose(f); return rc; }
+    const uint64_t n = h.n_rows, C = 1u << 16;
+    std::vector<uint8_t> valid(n ? n : 1);
+    bool ok = n == 0 || fread(valid.data(), 1, n, f) == n;
+    float *pin = nullptr;
+    if (ok && n) ok = cudaHostAlloc(&pin, C * h.dim * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+    for (uint64_t at = 0; ok && at < n; at += C) {
+        const uint64_t m = (n - at) < C ? (n - at) : C;
+        ok = fread(pin, sizeof(float), m * h.dim, f) == m * h.dim;
+        if (ok) {
+            rc = sema_index_append(s, pin, m, valid.data() + at, /*normalize=*/0, nullptr);   // rows are stored normalised
+            ok = rc == SEMA_OK;
+        }
+    }
+    if (pin) cudaFreeHost(pin);
+    fclose(f);
+    if (!ok) {
+        sema_index_destroy(s);
+        return rc ? rc : fail(SEMA_ERR_INVALID, "%s is truncated", path);
+    }
+    *out = s;
     return SEMA_OK;
 }
 

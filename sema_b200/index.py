@@ -93,6 +93,29 @@ class GpuIndex:
         r = np.ascontiguousarray(rows, dtype=np.uint64)
         check(self._L.sema_index_tombstone(self._h, _ptr(r), r.shape[0]))
 
+    def compact(self) -> np.ndarray:
+        """Drop null / tombstoned rows; returns new_row_of_old (uint64, 2**64-1 = dropped)."""
+        n = len(self)
+        m = np.zeros(max(n, 1), dtype=np.uint64)
+        live = C.c_uint64()
+        check(self._L.sema_index_compact(self._h, _ptr(m), C.byref(live)))
+        return m[:n]
+
+    def save(self, path: str) -> None:
+        check(self._L.sema_index_save(self._h, path.encode("utf-8")))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, capacity_rows: int = 0) -> "GpuIndex":
+        L = _lib.lib()
+        h = C.c_void_p()
+        check(L.sema_index_load(path.encode("utf-8"), device, capacity_rows, C.byref(h)))
+        self = cls.__new__(cls)
+        self._L, self._h = L, h
+        self.dim = int(L.sema_index_dim(h))
+        self.device = device
+        self.metric = None
+        return self
+
     # -- search (K2 / K3) -----------------------------------------------------------
     def search(self, q: np.ndarray, k: int):
         """-> (row_ids uint64[n_found], scores float32[n_found]) best first."""

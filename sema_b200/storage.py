@@ -60,6 +60,7 @@ STORE_SIGNATURES = {
     "sema_store_group_results_by_file": (C.c_int, [_vp, C.POINTER(_Hit), C.c_uint32, C.POINTER(_Grouped), C.c_uint32,
                                                    C.POINTER(C.c_uint32)]),
     "sema_store_remove_file_chunks": (C.c_int, [_vp, C.c_char_p, _u64p]),
+    "sema_store_compact": (C.c_int, [_vp, _u64p]),
     "sema_store_chunk": (C.c_int, [_vp, C.c_uint64, _cpp, _cpp, _u64p, _u64p, _cpp]),
     "sema_store_len": (C.c_uint64, [_vp]),
     "sema_store_last_error": (C.c_char_p, []),
@@ -220,6 +221,12 @@ class StorageManager:
         removed = C.c_uint64()
         _check(self._lib.sema_store_remove_file_chunks(self._h, file_path.encode("utf-8"), C.byref(removed)))
         return removed.value
+
+    def compact(self) -> int:
+        """Drop removed chunks and renumber rows; returns the live chunk count."""
+        n = C.c_uint64()
+        _check(self._lib.sema_store_compact(self._h, C.byref(n)))
+        return n.value
 
     def __len__(self) -> int:
         return int(self._lib.sema_store_len(self._h))

@@ -504,3 +504,82 @@ def test_shard_group_world1_equals_plain_search(sema, oracle_c):
                 g.search(Q[0], 200)                      # the fused exchange covers k <= 128
         finally:
             g.close()
+
+
+# ---------------------------------------------------------------- next rows: compaction, disk cache, Arrow
+def test_compaction_drops_dead_rows_and_keeps_order(sema, oracle_c):
+    n, d, k = 20000, 384, 10
+    X = _unit(1, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::9] = 0
+    Q = _unit(2, 6, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, valid=valid, normalize=False)
+        dead = np.arange(5, n, 13, dtype=np.uint64)
+        idx.tombstone(dead)
+        valid[dead.astype(np.int64)] = 0
+        mapping = idx.compact()
+        live_rows = np.nonzero(valid)[0]
+        assert len(idx) == len(live_rows)
+        assert np.array_equal(mapping[live_rows], np.arange(len(live_rows), dtype=np.uint64))
+        assert (mapping[valid == 0] == np.uint64(2**64 - 1)).all()
+        assert np.array_equal(idx.read_rows(0, len(live_rows)), X[live_rows])
+        Xc = X[live_rows]
+        for q in Q:
+            ids, sc = idx.search(q, k)
+            r_ids, r_sc = oracle_c.scan(Xc, q, k)
+            O.check_parity(ids, sc, r_ids, r_sc)
+        idx.set_batch_mode(2)                               # K3 planes are re-tiled after the move
+        bids, bsc, bnf = idx.search_batch(Q, k)
+        for i, q in enumerate(Q):
+            r_ids, r_sc = oracle_c.scan(Xc, q, k)
+            O.check_parity(bids[i], bsc[i], r_ids, r_sc)
+        first = idx.append(X[:100], normalize=False)        # the freed capacity is usable again
+        assert first == len(live_rows)
+
+
+def test_save_and_load_round_trip(sema, oracle_c, tmp_path):
+    n, d, k = 5000, 130, 10                                 # padded rows (dim % 4 != 0)
+    X = _unit(1, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::17] = 0
+    q = _unit(2, 1, d)[0]
+    path = str(tmp_path / "chunks.semaidx")
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, valid=valid, normalize=False)
+        want = idx.search(q, k)
+        idx.save(path)
+    assert os.path.getsize(path) == 64 + n + n * d * 4
+    idx2 = sema.GpuIndex.load(path, capacity_rows=n + 10)
+    try:
+        got = idx2.search(q, k)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        assert len(idx2) == n and idx2.capacity == n + 10
+        r_ids, r_sc = oracle_c.scan(X, q, k, valid=valid)
+        O.check_parity(got[0], got[1], r_ids, r_sc)
+    finally:
+        idx2.close()
+    with pytest.raises(sema.SemaError):
+        sema.GpuIndex.load(str(tmp_path / "missing.semaidx"))
+
+
+def test_arrow_fixed_size_list_import(sema, oracle_c):
+    # the reference's vector column: FixedSizeList<Float32,384>, nullable (src/storage/lance_indexer.rs:41-45, 75-76)
+    import pyarrow as pa
+    from sema_b200.arrow_import import append_arrow
+    n, d = 3000, 384
+    X = _unit(1, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::5] = 0
+    vectors = [X[i].tolist() if valid[i] else None for i in range(n)]
+    arr = pa.array(vectors, type=pa.list_(pa.float32(), d))
+    assert arr.null_count == int((valid == 0).sum())
+    q = _unit(2, 1, d)[0]
+    with sema.GpuIndex(d, 2 * n) as idx:
+        assert append_arrow(idx, arr) == 0
+        assert append_arrow(idx, arr.slice(100, 50)) == n       # a sliced column (non-zero offset)
+        ids, sc = idx.search(q, 10)
+    Xall = np.concatenate([X, X[100:150]])
+    vall = np.concatenate([valid, valid[100:150]])
+    r_ids, r_sc = oracle_c.scan(Xall, q, 10, valid=vall)
+    O.check_parity(ids, sc, r_ids, r_sc)

@@ -131,3 +131,21 @@ def test_remove_file_chunks(world):
     O.check_parity(np.array([_row_of(chunks, c) for c, _ in after], dtype=np.uint64),
                    np.array([s for _, s in after], dtype=np.float32), r_ids, r_sc)
     assert all(c.file_path != victim for c, _ in mgr.search("## ", 1000)[:50])   # LIKE scan skips deleted rows too
+
+
+def test_store_compaction_keeps_null_chunks_and_drops_removed_files():
+    from sema_b200.storage import Chunk, StorageManager
+    with StorageManager(dim=corpus.DIM, capacity_rows=64, embedder=corpus.embed) as m:
+        cs = [Chunk(f"f{i % 3}.md:{i}", f"f{i % 3}.md", i + 1, i + 1, t) for i, t in enumerate(
+            ["vector index search", "--- ***", "kernel memory bandwidth", "tensor shard merge", "cache latency",
+             "???", "storage engine table"])]
+        m.index_chunks(cs)
+        assert m.remove_file_chunks("f1.md") == 2              # chunks 1 and 4
+        assert m.compact() == 5
+        assert len(m) == 5
+        ids = [m.chunk(r).id for r in range(5)]
+        assert ids == ["f0.md:0", "f2.md:2", "f0.md:3", "f2.md:5", "f0.md:6"]
+        got = m.search("tensor shard", 10)
+        assert got[0][0].id == "f0.md:3"
+        assert sorted(c.id for c, _ in got) == ["f0.md:0", "f0.md:3", "f0.md:6", "f2.md:2"]   # the null chunk never matches
+        assert [c.id for c, _ in m.search("???", 10)] == ["f2.md:5"]                           # ... but LIKE still finds it
