@@ -528,6 +528,13 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     shard_rows = hi - lo
+    traffic = None
+    try:   # DRAM bytes per launch from the committed `ncu --set full` capture of this exact workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if world == 1 and a.k == 10:
+            traffic = tr.get(f"k2_single_{a.rows}x{a.dim}")
+    except Exception:
+        pass
     bytes_per_launch = shard_rows * a.dim * 4          # algorithmic bytes: the shard read once
     achieved = bytes_per_launch / (ms_step * 1e-3) / 1e9
     line = {
@@ -545,7 +552,8 @@ def run_ours(a):
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": pk_src,
+            "traffic": traffic, "traffic_source": "profiles/r01_k2_scan_full_raw.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None,
+            "algorithmic_bytes": bytes_per_launch, "peak_source": pk_src,
             "kernel": "scan_topk_kernel (K2)",
             "note": "achieved = rows_per_gpu*dim*4 bytes / device time per step (one K2 launch per step"
                     + ("" if world == 1 else ", which includes the top-k exchange and the global merge") + ")",

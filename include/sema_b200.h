@@ -109,10 +109,11 @@ int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_i
 int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row_ids,
                       float *scores, uint32_t *n_found);
 /* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq].  With the
- * cosine metric, dim % 64 == 0, dim <= 384, k <= 100 and nq >= 4 this runs kernel K3 (tcgen05
- * tensor cores, bf16x3 split precision, exact fp32 re-scoring of the candidates; needs a second
- * dim*4 bytes per row of HBM for the bf16 planes, built on first use); otherwise, or if that
- * memory cannot be had, K2 runs once per query.  Results are identical either way. */
+ * cosine metric, dim % 64 == 0, dim <= 768, k <= 100 and nq >= 4 this runs kernel K3 (tcgen05
+ * tensor cores: bf16x3 split precision up to dim 384, a single bf16 pass for 384 < dim <= 768;
+ * exact fp32 re-scoring of the candidates; needs a second dim*4 bytes per row of HBM for the bf16
+ * planes, built on first use); otherwise, or if that memory cannot be had, K2 runs once per
+ * query.  Results are identical either way. */
 int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32_t k,
                             uint64_t *row_ids, float *scores, uint32_t *n_found);
 /* Same with queries and results resident on the device (Q_dev: nq x dim dense). */

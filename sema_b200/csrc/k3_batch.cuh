@@ -46,7 +46,8 @@ constexpr int STAGE_BYTES = 2 * STAGE_PLANE_BYTES;        // hi + lo = 16 KB
 constexpr int THREADS = 192;
 constexpr int EPI_THREADS = 128;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int MAX_DIM = 384;           // q_hi + q_lo need dim columns; 128 are the accumulators
+constexpr int MAX_DIM = 384;           // bf16x3: q_hi + q_lo need dim TMEM columns; 128 are the accumulators
+constexpr int MAX_DIM_1PASS = 768;     // single pass: q_hi alone needs dim/2 columns
 
 // bytes of the pre-tiled planes per 64-row tile
 __host__ __device__ constexpr size_t tile_bytes(int dim) { return (size_t)TILE_N * dim * 4; }
@@ -308,7 +309,7 @@ batch_scan_kernel(const Params p)
     // using the constant keeps every UMMA operand address in uniform registers.
     if (*tmem_slot != 0) __trap();
     constexpr uint32_t tmem = 0;
-    const uint32_t acc_col = 2 * acols;      // accumulators follow the two query planes
+    const uint32_t acc_col = PASSES == 3 ? 2 * acols : acols;   // accumulators follow the query plane(s)
     const uint32_t crank = C > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t cmask = (uint16_t)((1u << C) - 1u);
     constexpr uint32_t SLICE = STAGE / C;

@@ -298,10 +298,14 @@ constexpr uint32_t K3_MAX_K = 100;
 constexpr float K3_ERR_REL = 2.5e-4f;  // >= 3*2^-16 (dropped split terms) + fp32 accumulation over 3*dim terms
 constexpr float K3_ERR_REL_1PASS = 8.5e-3f;  // >= 2*2^-8 + 2^-16 (both operands rounded to bf16) + accumulation
 
-bool k3_shape_ok(const sema_index *s, uint32_t k)
+// passes the batch would run with: bf16x3 up to dim 384 (TMEM holds q_hi and q_lo), the single-pass
+// filter up to dim 768 (q_hi only) or when asked for (batch mode 3); 0 = K3 cannot serve this shape
+int k3_passes(const sema_index *s, uint32_t k)
 {
-    return s->metric == SEMA_METRIC_COSINE && s->dim % k3::BLOCK_K == 0 && s->dim <= (uint32_t)k3::MAX_DIM &&
-           k <= K3_MAX_K && !s->planes_failed;
+    if (s->metric != SEMA_METRIC_COSINE || s->dim % k3::BLOCK_K != 0 || k > K3_MAX_K || s->planes_failed) return 0;
+    if (s->dim <= (uint32_t)k3::MAX_DIM) return s->batch_mode == 3 ? 1 : 3;
+    if (s->dim <= (uint32_t)k3::MAX_DIM_1PASS) return 1;
+    return 0;
 }
 
 // Bring the bf16 planes up to date with rows [0, n).  Tombstones invalidate from their row on.
@@ -411,7 +415,7 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
              uint32_t *nf_d)
 {
     const uint32_t kc = k <= 16 ? 32 : (k <= 48 ? 64 : 128);
-    const int passes = s->batch_mode == 3 ? 1 : 3;
+    const int passes = k3_passes(s, k);
     const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
     const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
     int rc;
@@ -507,7 +511,7 @@ int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t
                uint32_t *nf_d)
 {
     const bool want_k3 = s->batch_mode >= 2 || (s->batch_mode == 0 && nq >= 4);
-    if (want_k3 && k3_shape_ok(s, k)) {
+    if (want_k3 && k3_passes(s, k) != 0) {
         int rc = k3_sync_planes(s, n);
         if (rc == SEMA_OK) return k3_batch(s, Qd, nq, n, k, ids_d, sc_d, nf_d);
         if (rc != SEMA_ERR_NOMEM) return rc;

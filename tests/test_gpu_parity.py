@@ -461,15 +461,37 @@ def test_k3_null_rows_appends_and_tombstones(sema, oracle_c):
 
 
 def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
-    # dim 768 and the L2 metric are served by K2 (one pass per query): same results
-    X = _unit(1, 5000, 768)
-    Q = _unit(2, 9, 768)
-    with sema.GpuIndex(768, 5000) as idx:
+    # dim 1024 and the L2 metric are served by K2 (one pass per query): same results
+    X = _unit(1, 5000, 1024)
+    Q = _unit(2, 9, 1024)
+    with sema.GpuIndex(1024, 5000) as idx:
         idx.append(X, normalize=False)
         ids, sc, nf = idx.search_batch(Q, 10)
         assert idx.batch_stats()[0] == 0
     r = oracle_c.scan_batch(X, Q, 10)
     for i in range(9):
+        O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+    X = _unit(1, 5000, 384)
+    with sema.GpuIndex(384, 5000, metric=1) as idx:
+        idx.append(X, normalize=False)
+        Q = _unit(2, 9, 384)
+        ids, sc, nf = idx.search_batch(Q, 10)
+        assert idx.batch_stats()[0] == 0
+    r = oracle_c.scan_batch(X, Q, 10, metric=1)
+    for i in range(9):
+        O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+    # dim 768 (config 5's width): K3 with the single bf16 pass, k = 100
+    X = _unit(1, 40000, 768)
+    Q = _unit(2, 130, 768)
+    with sema.GpuIndex(768, 40000) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, 100)
+        assert idx.batch_stats() == (130, 0)
+        idx.set_batch_mode(1)
+        ids2, sc2, nf2 = idx.search_batch(Q, 100)
+    assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
+    r = oracle_c.scan_batch(X, Q, 100)
+    for i in range(130):
         O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
     X = _unit(1, 5000, 384)
     Q = _unit(2, 9, 384)
