@@ -48,9 +48,10 @@ def parse():
     ap.add_argument("--variant", type=int, default=-1, help="K2 kernel variant (tuning)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused = P2P stores + merge inside K2's last block; nccl = all-gather + K4")
-    ap.add_argument("--workload", default="single", choices=["single", "batch", "ingest"],
+    ap.add_argument("--workload", default="single", choices=["single", "batch", "ingest", "config1"],
                     help="single = headline single-query scan (K2); batch = BASELINE config 3, nq-query batches (K3); "
-                         "ingest = BASELINE config 4/5 style streaming ingest (K1) interleaved with queries")
+                         "ingest = BASELINE config 4/5 style streaming ingest (K1) interleaved with queries; "
+                         "config1 = ~10k-chunk synthetic markdown corpus through the StorageManager boundary")
     ap.add_argument("--ingest-batch", type=int, default=65536, help="rows per appended batch (--workload ingest)")
     ap.add_argument("--queries-per-batch", type=int, default=2, help="searches issued after each appended batch")
     ap.add_argument("--nq", type=int, default=1024, help="queries per batch (--workload batch)")
@@ -354,6 +355,69 @@ def run_ingest(a):
     print(json.dumps(line), flush=True)
 
 
+def run_config1(a):
+    """BASELINE.json configs[0]: index + search over a small synthetic markdown corpus (~10k chunks,
+    384-d, top-10) through the StorageManager boundary, next to the CPU oracle on the same vectors.
+    The embedder is a deterministic STAND-IN (oracle/corpus.py): the reference's MiniLM model and
+    ONNX Runtime are not available offline, so embedding time is excluded from both arms."""
+    from oracle import corpus, c_oracle          # corpus builder + CPU arm (test infrastructure)
+    from sema_b200 import _lib
+    from sema_b200.storage import Chunk, StorageManager
+
+    if _lib.lib().sema_device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: sema_b200 has no CPU fallback")
+    files = corpus.make_markdown_tree(1050, seed=3)
+    chunks = [Chunk(c["id"], c["file_path"], c["start_line"], c["end_line"], c["content"]) for c in corpus.chunk_tree(files)]
+    emb = np.stack([corpus.embed(c.content) for c in chunks])
+    rng = np.random.default_rng(5)
+    queries = [" ".join(corpus._WORDS[int(i)] for i in rng.integers(0, len(corpus._WORDS), 6)) for _ in range(100)]
+    qvec = {q: corpus.embed(q) for q in queries}
+    k = a.k
+    with StorageManager(dim=corpus.DIM, capacity_rows=len(chunks) + 64, normalize=True,
+                        embedder=lambda t: qvec.get(t)) as mgr:
+        t0 = time.perf_counter()
+        mgr.index_chunks(chunks, vectors=emb)
+        t_index = time.perf_counter() - t0
+        for q in queries[:10]:
+            mgr.search(q, k)
+        lat = []
+        for q in queries:
+            t0 = time.perf_counter()
+            hits = mgr.search(q, k)
+            lat.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for q in queries:
+            mgr.execute_search(q)
+        t_exec = (time.perf_counter() - t0) / len(queries)
+    X = c_oracle.normalize(emb)
+    Qn = c_oracle.normalize(np.stack([qvec[q] for q in queries]))
+    for q in Qn[:5]:
+        c_oracle.scan(X, q, k)
+    cl = []
+    for q in Qn:
+        t0 = time.perf_counter()
+        c_oracle.scan(X, q, k)
+        cl.append(time.perf_counter() - t0)
+    ids_ok = [c.id for c, _ in hits] == [chunks[int(i)].id for i in c_oracle.scan(X, Qn[-1], k)[0]]
+    line = {
+        "metric": f"config1_search_latency_top{k}_{len(chunks)}_chunks_384d", "value": 1.0 / float(np.median(lat)),
+        "unit": "queries/s", "n_gpus": 1, "steps": len(queries), "warmup": 10, "ms_per_step": float(np.median(lat)) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{len(files)} synthetic markdown files -> {len(chunks)} chunks (reference chunker constants), "
+                               f"stand-in embedder (NOT MiniLM), 100 seeded queries, top-{k}, through StorageManager.search",
+                   "index_chunks_s": t_index},
+        "latency_ms": {"gpu_search_median": float(np.median(lat)) * 1e3, "gpu_search_p99": float(np.percentile(lat, 99)) * 1e3,
+                       "gpu_execute_search_mean": t_exec * 1e3,
+                       "cpu_oracle_median": float(np.median(cl)) * 1e3, "cpu_oracle_p99": float(np.percentile(cl, 99)) * 1e3,
+                       "cpu_threads": c_oracle.threads()},
+        "cpu_baseline": {"value": 1.0 / float(np.median(cl)), "unit": "queries/s", "cores": c_oracle.threads(), "kind": "port",
+                         "sample": "oracle/cpu_scan.c on the same normalised vectors and queries (whole workload, not a sample)"},
+        "e2e": {"value": 1.0 / float(np.median(lat)), "unit": "queries/s", "h2d_bytes_per_step": 1536, "d2h_bytes_per_step": 8 + 12 * k},
+        "last_query_matches_oracle": bool(ids_ok),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(a):
     import torch
 
@@ -584,6 +648,8 @@ def main():
         run_batch(a)
     elif a.workload == "ingest":
         run_ingest(a)
+    elif a.workload == "config1":
+        run_config1(a)
     else:
         run_ours(a)
 
