@@ -27,8 +27,8 @@
 // MMA against the epilogue.  Each epilogue thread owns one query (= one TMEM lane): it
 // reads its 64 scores with tcgen05.ld and keeps a private candidate list in shared memory.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (224 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer 0,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4), warp 6 = MMA issuer 1.
 #pragma once
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -43,7 +43,7 @@ constexpr int BLOCK_K = 64;            // k elements per pipeline stage
 constexpr int UMMA_K = 16;             // k per tcgen05.mma (bf16)
 constexpr int STAGE_PLANE_BYTES = TILE_N * BLOCK_K * 2;   // 8 KB: one plane of one stage
 constexpr int STAGE_BYTES = 2 * STAGE_PLANE_BYTES;        // hi + lo = 16 KB
-constexpr int THREADS = 192;
+constexpr int THREADS = 224;
 constexpr int EPI_THREADS = 128;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_DIM = 384;           // bf16x3: q_hi + q_lo need dim TMEM columns; 128 are the accumulators
@@ -252,30 +252,35 @@ struct Params {
 // PASSES = 3: bf16x3 split (hi.hi + lo.hi + hi.lo), a stage holds the hi and lo plane blocks.
 // PASSES = 1: single bf16 pass as a coarser candidate filter (only the hi plane block is fetched;
 //             the exactness proof then uses the 1-pass error bound and falls back more readily).
-template <int KC, int PASSES>
+// QT = query tiles (of 128) per CTA.  The single-pass mode leaves room in TMEM for a second query
+// tile (2 x dim/2 columns): both tiles consume the same shared-memory stages, which halves the
+// operand bytes delivered per MMA (the L2->SM delivery rate is what bounds that mode), and their
+// two accumulators ping-pong between the MMA and the epilogue.
+template <int KC, int PASSES, int QT = 1>
 struct Smem {
+    static_assert(QT == 1 || PASSES == 1, "two query tiles per CTA only fit TMEM in the single-pass mode");
     static constexpr int STAGE = PASSES == 3 ? STAGE_BYTES : STAGE_PLANE_BYTES;
-    static constexpr int LIST_BYTES = KC * TILE_Q * 8;     // scores f32 + rows u32
+    static constexpr int LIST_BYTES = QT * KC * TILE_Q * 8;     // scores f32 + rows u32, per query tile
     static constexpr int BAR_BYTES = 1024;
     static constexpr int STAGES_RAW = (227 * 1024 - LIST_BYTES - BAR_BYTES) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 24 ? 24 : STAGES_RAW;
     static constexpr int TOTAL = STAGES * STAGE + LIST_BYTES + BAR_BYTES;
 };
 
-// C = CTAs per cluster.  The C CTAs of a cluster hold C different query tiles and stream the
+// C = CTAs per cluster (QT and PASSES: see Smem).  The C CTAs of a cluster hold C different query tiles and stream the
 // same corpus tiles: every stage is fetched once per cluster (each CTA issues 1/C of it) and
 // multicast into all C shared memories, cutting the L2->SM operand traffic C-fold.
-template <int KC, int C, int PASSES>
+template <int KC, int C, int PASSES, int QT>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_kernel(const Params p)
 {
-    using S = Smem<KC, PASSES>;
+    using S = Smem<KC, PASSES, QT>;
     constexpr int STAGES = S::STAGES;
     constexpr int STAGE = S::STAGE;          // bytes fetched per k-block
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem;
-    float *list_sc = reinterpret_cast<float *>(smem + STAGES * STAGE);              // [KC][128]
-    uint32_t *list_row = reinterpret_cast<uint32_t *>(list_sc + KC * TILE_Q);       // [KC][128]
+    float *list_sc = reinterpret_cast<float *>(smem + STAGES * STAGE);              // [QT][KC][128]
+    uint32_t *list_row = reinterpret_cast<uint32_t *>(list_sc + QT * KC * TILE_Q);  // [QT][KC][128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE + S::LIST_BYTES);
     uint64_t *full = bars;                    // [STAGES]  TMA -> MMA
     uint64_t *empty = bars + STAGES;          // [STAGES]  MMA -> TMA
@@ -284,7 +289,7 @@ batch_scan_kernel(const Params p)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t qt = blockIdx.x, part = blockIdx.y;
+    const uint32_t qt = blockIdx.x, part = blockIdx.y;   // this CTA's query tiles: qt*QT .. qt*QT + QT-1
     const uint32_t kblocks = p.dim / BLOCK_K;            // stages per tile
     const uint32_t acols = p.dim / 2;                    // TMEM columns per query plane
     // contiguous tile range of this row partition
@@ -292,7 +297,8 @@ batch_scan_kernel(const Params p)
     const uint32_t t0 = min(part * per, p.n_tiles), t1 = min(t0 + per, p.n_tiles);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], C); }
+        // a stage is released by one issuer per CTA of the cluster (QT = 1) or by both (QT = 2)
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], C * QT); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -309,32 +315,36 @@ batch_scan_kernel(const Params p)
     // using the constant keeps every UMMA operand address in uniform registers.
     if (*tmem_slot != 0) __trap();
     constexpr uint32_t tmem = 0;
-    const uint32_t acc_col = PASSES == 3 ? 2 * acols : acols;   // accumulators follow the query plane(s)
+    // TMEM columns: [query planes: hi (+ lo) for bf16x3, or QT hi planes][2 accumulators of 64]
+    const uint32_t acc_col = PASSES == 3 ? 2 * acols : QT * acols;
     const uint32_t crank = C > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t cmask = (uint16_t)((1u << C) - 1u);
     constexpr uint32_t SLICE = STAGE / C;
 
-    // ---- epilogue warps stage the query tile into TMEM (A operand): row m <-> lane m
-    if (warp >= 2) {
+    // ---- epilogue warps stage the query tile(s) into TMEM (A operand): row m <-> lane m
+    if (warp >= 2 && warp <= 5) {
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
-        const float *q = p.Q + ((size_t)qt * TILE_Q + m) * p.dim;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-        for (uint32_t c = 0; c < p.dim; c += 16) {
-            float v[16];
+#pragma unroll 1
+        for (int qi = 0; qi < QT; ++qi) {
+            const float *q = p.Q + (((size_t)qt * QT + qi) * TILE_Q + m) * p.dim;
+            for (uint32_t c = 0; c < p.dim; c += 16) {
+                float v[16];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float4 f = *reinterpret_cast<const float4 *>(q + c + 4 * e);
-                v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
-            }
-            uint32_t hi[8], lo[8];
+                for (int e = 0; e < 4; ++e) {
+                    const float4 f = *reinterpret_cast<const float4 *>(q + c + 4 * e);
+                    v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
+                }
+                uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-                lo[e] = pack_bf16(v[2 * e] - bf16_round(v[2 * e]), v[2 * e + 1] - bf16_round(v[2 * e + 1]));
+                for (int e = 0; e < 8; ++e) {
+                    hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+                    lo[e] = pack_bf16(v[2 * e] - bf16_round(v[2 * e]), v[2 * e + 1] - bf16_round(v[2 * e + 1]));
+                }
+                tmem_st8(lane_addr + qi * acols + c / 2, hi);
+                if (PASSES == 3) tmem_st8(lane_addr + acols + c / 2, lo);
             }
-            tmem_st8(lane_addr + c / 2, hi);
-            if (PASSES == 3) tmem_st8(lane_addr + acols + c / 2, lo);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -343,8 +353,8 @@ batch_scan_kernel(const Params p)
     tc_fence_after();
 
     if (warp == 0) {
-        // ===== TMA producer: one contiguous 16 KB bulk copy per stage (whole warp converged,
-        // one elected lane issues) =====
+        // ===== TMA producer: one contiguous bulk copy per stage (whole warp converged, one elected
+        // lane issues) =====
         {
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = t0; t < t1; ++t) {
@@ -358,30 +368,41 @@ batch_scan_kernel(const Params p)
                     else
                         bulk_g2s_multicast(ring + stage * STAGE + crank * SLICE,
                                            src + (size_t)kb * STAGE_BYTES + crank * SLICE, SLICE, &full[stage], cmask);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===== MMA issuer: 3 UMMAs per k-step (hi.hi, lo.hi, hi.lo).  The warp stays converged so
-        // that descriptors and TMEM addresses live in uniform registers; one elected lane issues =====
-        {
-            constexpr uint32_t idesc = make_idesc();
-            uint32_t stage = 0, phase = 0;
-            uint32_t it = 0;
-            for (uint32_t t = t0; t < t1; ++t, ++it) {
-                const uint32_t buf = it & 1, use = it >> 1;
+    } else if (warp == 1 || warp == 6) {
+        // ===== MMA issuers (two warps: one elected lane of one warp cannot issue a 128x64x16 UMMA
+        // every 32 cycles, two can).  Issuer w owns accumulator buffer w: with QT = 1 it takes the
+        // corpus tiles of parity w, with QT = 2 it takes query tile w of every corpus tile (both
+        // issuers then consume every stage, which is released after both commits).  Per k-step 3
+        // UMMAs (hi.hi, lo.hi, hi.lo) or 1 (single pass).  The warp stays converged so that
+        // descriptors and TMEM addresses live in uniform registers. =====
+        const uint32_t w = warp == 1 ? 0u : 1u;
+        constexpr uint32_t idesc = make_idesc();
+        // Two issuers need the ring to hold two whole tiles when they work on different tiles
+        // (an mbarrier waiter may be at most one phase ahead); otherwise issuer 0 works alone.
+        const bool dual = QT == 2 || 2 * kblocks <= (uint32_t)STAGES;
+        const uint32_t a_base = tmem + (QT == 2 ? w * acols : 0u);
+        const uint32_t tstep = (QT == 1 && dual) ? 2u : 1u;
+        uint32_t st = 0, ph = 0, it = 0;
+        if (QT == 1 && dual && w == 1) st = kblocks;   // the first tile belongs to issuer 0
+        if (dual || w == 0) {
+            for (uint32_t t = t0 + ((QT == 1 && dual) ? w : 0u); t < t1; t += tstep, ++it) {
+                const uint32_t buf = dual ? w : (it & 1);
+                const uint32_t use = dual ? it : (it >> 1);
+                const uint32_t d_tmem = tmem + acc_col + buf * TILE_N;
                 mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem + acc_col + buf * TILE_N;
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(&full[st], ph);
                     tc_fence_after();
-                    const uint32_t sb = smem_u32(ring + stage * STAGE);
+                    const uint32_t sb = smem_u32(ring + st * STAGE);
 #pragma unroll
                     for (int j = 0; j < BLOCK_K / UMMA_K; ++j) {
-                        const uint32_t a_hi = tmem + kb * (BLOCK_K / 2) + j * (UMMA_K / 2);
+                        const uint32_t a_hi = a_base + kb * (BLOCK_K / 2) + j * (UMMA_K / 2);
                         const uint32_t a_lo = a_hi + acols;
                         const uint64_t b_hi = make_b_desc(sb + j * 2 * (TILE_N * 16), TILE_N * 16, 128);
                         const uint64_t b_lo = make_b_desc(sb + STAGE_PLANE_BYTES + j * 2 * (TILE_N * 16), TILE_N * 16, 128);
@@ -391,80 +412,101 @@ batch_scan_kernel(const Params p)
                             umma_ts(d_tmem, a_hi, b_lo, idesc, 1);
                         }
                     }
-                    if (C == 1) umma_commit(&empty[stage]);   // frees the smem stage when the MMAs retire
-                    else umma_commit_multicast(&empty[stage], cmask);   // ... in every CTA of the cluster
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (C == 1) umma_commit(&empty[st]);   // frees the smem stage when the MMAs retire
+                    else umma_commit_multicast(&empty[st], cmask);   // ... in every CTA of the cluster
+                    if (++st == (uint32_t)STAGES) { st = 0; ph ^= 1; }
                 }
-                umma_commit(&acc_full[buf]);             // accumulator ready for the epilogue
+                umma_commit(&acc_full[buf]);           // accumulator ready for the epilogue
+                if (QT == 1 && dual) {                 // skip the other issuer's tile
+                    st += kblocks;
+                    if (st >= (uint32_t)STAGES) { st -= STAGES; ph ^= 1; }
+                }
             }
         }
         __syncwarp();
     } else {
-        // ===== epilogue: thread m owns query m; private candidate list in shared memory =====
+        // ===== epilogue: thread m owns query m of each of the CTA's query tiles; private candidate
+        // lists in shared memory =====
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + acc_col;
-        float thr = -INFINITY;   // lowest score kept once the list is full
-        int cnt = 0, min_pos = 0;
+        float thr0 = -INFINITY, thr1 = -INFINITY;   // lowest score kept once the list is full
+        int cnt0 = 0, cnt1 = 0, mp0 = 0, mp1 = 0;
         uint32_t it = 0;
         for (uint32_t t = t0; t < t1; ++t, ++it) {
-            const uint32_t buf = it & 1, use = it >> 1;
-            mbar_wait(&acc_full[buf], use & 1);
-            tc_fence_after();
-            uint32_t r[2][32];
-            tmem_ld32(lane_addr + buf * TILE_N, r[0]);
-            tmem_ld32(lane_addr + buf * TILE_N + 32, r[1]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);   // MMA may overwrite this accumulator
-            const uint32_t row0 = t * TILE_N;
-            // Pass 1 (unrolled, branch-free): which of my 64 scores beat the admission threshold?
-            uint32_t mask[2] = {0u, 0u};
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    mask[h] |= (__uint_as_float(r[h][c]) > thr) ? (1u << c) : 0u;
-            const uint32_t live = p.n_rows - row0;           // rows of this tile that exist (>= 1)
-            if (live < 32) { mask[0] &= (1u << live) - 1u; mask[1] = 0u; }
-            else if (live < 64) mask[1] &= (1u << (live - 32)) - 1u;
-            // Pass 2 (rare, not unrolled: keeps the instruction footprint small): insert them.
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t mk = mask[h];
 #pragma unroll 1
-                while (mk) {
-                    const int c = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    uint32_t bits = 0;
+            for (int qi = 0; qi < QT; ++qi) {
+                const uint32_t buf = QT == 1 ? (it & 1) : (uint32_t)qi;
+                const uint32_t use = QT == 1 ? (it >> 1) : it;
+                float thr = qi ? thr1 : thr0;
+                int cnt = qi ? cnt1 : cnt0, min_pos = qi ? mp1 : mp0;
+                float *lsc = list_sc + qi * KC * TILE_Q;
+                uint32_t *lrow = list_row + qi * KC * TILE_Q;
+                mbar_wait(&acc_full[buf], use & 1);
+                tc_fence_after();
+                uint32_t r[2][32];
+                tmem_ld32(lane_addr + buf * TILE_N, r[0]);
+                tmem_ld32(lane_addr + buf * TILE_N + 32, r[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);   // MMA may overwrite this accumulator
+                const uint32_t row0 = t * TILE_N;
+                // Pass 1 (unrolled, branch-free): which of my 64 scores beat the admission threshold?
+                uint32_t mask[2] = {0u, 0u};
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) bits = (e == c) ? r[h][e] : bits;   // register select
-                    const float v = __uint_as_float(bits);
-                    if (!(v > thr)) continue;                 // the threshold may have risen meanwhile
-                    const int slot = cnt < KC ? cnt : min_pos;
-                    list_sc[slot * TILE_Q + m] = v;
-                    list_row[slot * TILE_Q + m] = row0 + h * 32 + c;
-                    if (cnt < KC) ++cnt;
-                    if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
-                        float mn = list_sc[m];
-                        int mp = 0;
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        mask[h] |= (__uint_as_float(r[h][c]) > thr) ? (1u << c) : 0u;
+                const uint32_t live = p.n_rows - row0;           // rows of this tile that exist (>= 1)
+                if (live < 32) { mask[0] &= (1u << live) - 1u; mask[1] = 0u; }
+                else if (live < 64) mask[1] &= (1u << (live - 32)) - 1u;
+                // Pass 2 (rare, not unrolled: keeps the instruction footprint small): insert them.
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t mk = mask[h];
+#pragma unroll 1
+                    while (mk) {
+                        const int c = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        uint32_t bits = 0;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) bits = (e == c) ? r[h][e] : bits;   // register select
+                        const float v = __uint_as_float(bits);
+                        if (!(v > thr)) continue;                 // the threshold may have risen meanwhile
+                        const int slot = cnt < KC ? cnt : min_pos;
+                        lsc[slot * TILE_Q + m] = v;
+                        lrow[slot * TILE_Q + m] = row0 + h * 32 + c;
+                        if (cnt < KC) ++cnt;
+                        if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
+                            float mn = lsc[m];
+                            int mp = 0;
 #pragma unroll 8
-                        for (int i = 1; i < KC; ++i) {
-                            const float sv = list_sc[i * TILE_Q + m];
-                            if (sv < mn) { mn = sv; mp = i; }
+                            for (int i = 1; i < KC; ++i) {
+                                const float sv = lsc[i * TILE_Q + m];
+                                if (sv < mn) { mn = sv; mp = i; }
+                            }
+                            thr = mn;
+                            min_pos = mp;
                         }
-                        thr = mn;
-                        min_pos = mp;
                     }
                 }
+                if (qi) { thr1 = thr; cnt1 = cnt; mp1 = min_pos; }
+                else { thr0 = thr; cnt0 = cnt; mp0 = min_pos; }
             }
         }
-        // publish this partition's candidates for the query
-        const size_t q = (size_t)qt * TILE_Q + m;
-        uint32_t *out = p.cand_rows + (q * p.parts + part) * KC;
-        for (int i = 0; i < KC; ++i) out[i] = i < cnt ? list_row[i * TILE_Q + m] : 0xffffffffu;
-        p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr : -INFINITY;
+        // publish this partition's candidates for the CTA's queries
+#pragma unroll 1
+        for (int qi = 0; qi < QT; ++qi) {
+            const float thr = qi ? thr1 : thr0;
+            const int cnt = qi ? cnt1 : cnt0;
+            const uint32_t *lrow = list_row + qi * KC * TILE_Q;
+            const size_t q = ((size_t)qt * QT + qi) * TILE_Q + m;
+            uint32_t *out = p.cand_rows + (q * p.parts + part) * KC;
+            for (int i = 0; i < KC; ++i) out[i] = i < cnt ? lrow[i * TILE_Q + m] : 0xffffffffu;
+            p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr : -INFINITY;
+        }
     }
 
     tc_fence_before();

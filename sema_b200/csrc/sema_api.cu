@@ -96,6 +96,7 @@ struct sema_index {
     size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
     int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 bf16x3 whenever the shape allows, 3 K3 single bf16 pass
     int k3_cluster = 0;                 // 0 auto, else forced cluster size (1, 2, 4) — tuning
+    int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
     int normalize_queries = 0;          // apply K1 to host queries before scanning
     unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch]
     uint64_t k3_queries = 0, k3_fallbacks = 0;
@@ -335,19 +336,20 @@ int k3_sync_planes(sema_index *s, uint64_t n)
     return SEMA_OK;
 }
 
-template <int KC, int C, int PASSES>
-int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_tiles)
+// q_ctas = CTAs along the query axis (each owns QT query tiles)
+template <int KC, int C, int PASSES, int QT>
+int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_ctas)
 {
-    auto kern = k3::batch_scan_kernel<KC, C, PASSES>;
+    auto kern = k3::batch_scan_kernel<KC, C, PASSES, QT>;
     static bool attr_set[64] = {false};
     if (!attr_set[s->device & 63]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC, PASSES>::TOTAL));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC, PASSES, QT>::TOTAL));
         attr_set[s->device & 63] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(q_tiles, p.parts, 1);
+    cfg.gridDim = dim3(q_ctas, p.parts, 1);
     cfg.blockDim = dim3(k3::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = k3::Smem<KC, PASSES>::TOTAL;
+    cfg.dynamicSmemBytes = k3::Smem<KC, PASSES, QT>::TOTAL;
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -368,7 +370,7 @@ int k3_max_clusters(sema_index *s, int *out)
     static int cached[64] = {0};
     int &v = cached[s->device & 63];
     if (v == 0) {
-        auto kern = k3::batch_scan_kernel<KC, C, 3>;   // the 1-pass kernel uses no more shared memory
+        auto kern = k3::batch_scan_kernel<KC, C, 3, 1>;   // the single-pass kernels use no more shared memory
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC, 3>::TOTAL));
         if (C == 1) {
             v = s->num_sms;
@@ -393,16 +395,20 @@ int k3_max_clusters(sema_index *s, int *out)
     return SEMA_OK;
 }
 
-template <int KC, int PASSES>
-int k3_launch_scan_p(sema_index *s, const k3::Params &p, uint32_t q_tiles, int c)
+template <int KC, int PASSES, int QT>
+int k3_launch_scan_p(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c)
 {
-    return c == 4 ? k3_launch_scan_c<KC, 4, PASSES>(s, p, q_tiles)
-         : c == 2 ? k3_launch_scan_c<KC, 2, PASSES>(s, p, q_tiles) : k3_launch_scan_c<KC, 1, PASSES>(s, p, q_tiles);
+    return c == 4 ? k3_launch_scan_c<KC, 4, PASSES, QT>(s, p, q_ctas)
+         : c == 2 ? k3_launch_scan_c<KC, 2, PASSES, QT>(s, p, q_ctas) : k3_launch_scan_c<KC, 1, PASSES, QT>(s, p, q_ctas);
 }
 template <int KC>
-int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_tiles, int c, int passes)
+int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c, int passes, int qt)
 {
-    return passes == 1 ? k3_launch_scan_p<KC, 1>(s, p, q_tiles, c) : k3_launch_scan_p<KC, 3>(s, p, q_tiles, c);
+    if (passes == 3) return k3_launch_scan_p<KC, 3, 1>(s, p, q_ctas, c);
+    if constexpr (KC <= 64) {
+        if (qt == 2) return k3_launch_scan_p<KC, 1, 2>(s, p, q_ctas, c);
+    }
+    return k3_launch_scan_p<KC, 1, 1>(s, p, q_ctas, c);
 }
 template <int KC>
 int k3_clusters(sema_index *s, int c, int *out)
@@ -419,7 +425,18 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
     const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
     int rc;
-    const size_t qpad_rows = (size_t)(q_tiles_all + 3) / 4 * 4 * k3::TILE_Q;   // room for cluster padding
+    // QT query tiles per CTA (2 in the single-pass mode when there are at least 2 tiles), clusters of
+    // csize CTAs along the query axis: the query-tile count is padded to a multiple of QT*csize
+    // (Qpad rows beyond nq are zero queries whose results are never read).
+    // (two tiles need 2*dim/2 + 128 TMEM columns and two candidate lists in shared memory)
+    const int qt_per_cta = (passes == 1 && q_tiles_all >= 2 && s->k3_qt != 1 && s->dim <= 384 && kc <= 64) ? 2 : 1;
+    const uint32_t q_ctas_all = (q_tiles_all + qt_per_cta - 1) / qt_per_cta;
+    // measured on 10M x 384 x 1024q: bf16x3 is fastest with clusters of 4 (128 SMs, higher clocks under the
+    // power cap), the single-pass filter with clusters of 2 (144 SMs; it is bound by L2->SM delivery)
+    const int cpref = passes == 1 ? 2 : 4;
+    const int csize = s->k3_cluster > 0 ? s->k3_cluster : (q_ctas_all >= (uint32_t)cpref ? cpref : (q_ctas_all >= 2 ? 2 : 1));
+    const uint32_t q_ctas_pad = ((q_ctas_all + csize - 1) / csize) * csize;
+    const size_t qpad_rows = (size_t)q_ctas_pad * qt_per_cta * k3::TILE_Q;
     rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, qpad_rows * s->dim * sizeof(float));
     if (rc) return rc;
     if (s->flags_cap < nq) {
@@ -432,22 +449,16 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     CK(cudaMemsetAsync(s->Qpad_dev, 0, qpad_rows * s->dim * sizeof(float), s->stream));
     CK(cudaMemcpyAsync(s->Qpad_dev, Qd, (size_t)nq * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
 
-    // Cluster size C: C query tiles share one stream of corpus tiles (TMA multicast).  The
-    // query-tile count is padded to a multiple of C (Qpad rows beyond nq are zero queries).
-    // measured on 10M x 384 x 1024q: bf16x3 is fastest with clusters of 4 (128 SMs, higher clocks under the
-    // power cap), the single-pass filter with clusters of 2 (144 SMs; it is bound by L2->SM delivery)
-    const int cpref = passes == 1 ? 2 : 4;
-    const int csize = s->k3_cluster > 0 ? s->k3_cluster : (q_tiles_all >= (uint32_t)cpref ? cpref : (q_tiles_all >= 2 ? 2 : 1));
     int max_clusters = 1;
     rc = kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
     if (rc) return rc;
-    const uint32_t q_tiles_pad = ((q_tiles_all + csize - 1) / csize) * csize;
-    const uint32_t groups_all = q_tiles_pad / csize;             // clusters along the query axis
+    const uint32_t groups_all = q_ctas_pad / csize;             // clusters along the query axis
     // at most max_clusters cluster columns per launch; the clusters left over become row partitions
     for (uint32_t g0 = 0; g0 < groups_all; g0 += (uint32_t)max_clusters) {
         const uint32_t groups = (groups_all - g0) < (uint32_t)max_clusters ? (groups_all - g0) : (uint32_t)max_clusters;
-        const uint32_t qt0 = g0 * csize;
-        const uint32_t q_tiles = groups * csize;
+        const uint32_t q_ctas = groups * csize;                 // CTAs along the query axis in this launch
+        const uint32_t qt0 = g0 * csize * qt_per_cta;           // first query tile of this launch
+        const uint32_t q_tiles = q_ctas * qt_per_cta;
         uint32_t parts = (uint32_t)max_clusters / groups;
         if (parts > n_tiles) parts = n_tiles;
         if (parts < 1) parts = 1;
@@ -465,7 +476,8 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         p.n_tiles = n_tiles;
         p.parts = parts;
         p.dim = s->dim;
-        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_tiles, csize, passes) : kc == 64 ? k3_launch_scan<64>(s, p, q_tiles, csize, passes) : k3_launch_scan<128>(s, p, q_tiles, csize, passes);
+        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, csize, passes, qt_per_cta)
+                      : k3_launch_scan<128>(s, p, q_ctas, csize, passes, qt_per_cta);
         if (rc) return rc;
         const uint32_t q_first = qt0 * k3::TILE_Q;
         if (q_first >= nq) break;
@@ -1136,6 +1148,7 @@ uint64_t sema_index_launch_count(const sema_index *s) { return s ? s->launches :
 int sema_index_set_scan_variant(sema_index *s, int variant)
 {
     if (!s) return -1;
+    if (variant >= 200) { s->k3_qt = variant - 200; return variant; }        // 200 = auto, 201 = one query tile per CTA
     if (variant >= 100) { s->k3_cluster = variant - 100; return variant; }   // 100 = auto, 101/102/104 = K3 cluster size
     if (variant >= 0) s->variant = variant;
     return s->variant;
