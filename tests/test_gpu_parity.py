@@ -605,3 +605,40 @@ def test_arrow_fixed_size_list_import(sema, oracle_c):
     vall = np.concatenate([valid, valid[100:150]])
     r_ids, r_sc = oracle_c.scan(Xall, q, 10, valid=vall)
     O.check_parity(ids, sc, r_ids, r_sc)
+
+
+# ---------------------------------------------------------------- randomized sweep
+def test_randomized_shapes_against_oracle(sema, oracle_c):
+    """Seeded random sweep over ragged sizes, padded dims, both metrics, null rows, k up to 300,
+    single and batched searches: every result must satisfy the BASELINE acceptance rule."""
+    rng = np.random.default_rng(20261018)
+    dims = [4, 7, 50, 130, 384, 384, 384, 768, 1000]
+    for case in range(36):
+        d = int(rng.choice(dims))
+        n = int(rng.integers(1, 6000))
+        k = int(rng.choice([1, 3, 10, 32, 33, 50, 64, 100, 128, 129, 300]))
+        metric = int(rng.integers(0, 2))
+        X = _unit(100 + case, n, d)
+        valid = (rng.random(n) > 0.1).astype(np.uint8)
+        if rng.random() < 0.3:                               # duplicates -> exact ties
+            src = rng.integers(0, n, size=max(1, n // 20))
+            dst = rng.integers(0, n, size=len(src))
+            X[dst] = X[src]
+        nq = int(rng.choice([1, 2, 5, 9]))
+        Q = _unit(200 + case, nq, d)
+        if rng.random() < 0.5:
+            Q[0] = X[int(rng.integers(0, n))]
+        with sema.GpuIndex(d, n + 3, metric=metric) as idx:
+            half = n // 2
+            idx.append(X[:half], valid=valid[:half], normalize=False)
+            idx.append(X[half:], valid=valid[half:], normalize=False)
+            for i in range(nq):
+                ids, sc = idx.search(Q[i], k)
+                r_ids, r_sc = oracle_c.scan(X, Q[i], k, metric, valid)
+                assert len(ids) == len(r_ids), (case, d, n, k, metric)
+                O.check_parity(ids, sc, r_ids, r_sc)
+            bids, bsc, bnf = idx.search_batch(Q, k)
+            for i in range(nq):
+                r_ids, r_sc = oracle_c.scan(X, Q[i], k, metric, valid)
+                assert bnf[i] == len(r_ids)
+                O.check_parity(bids[i, :bnf[i]], bsc[i, :bnf[i]], r_ids, r_sc)
