@@ -1,0 +1,339 @@
+// api_batch.cu — K3: bf16 planes, cluster launch, exact re-scoring, K2 fallback; batched entry points.
+#include "index_impl.cuh"
+#include "k3_batch.cuh"
+
+using namespace sema;
+using namespace sema_impl;
+
+namespace {
+
+// ---- K3 dispatch -----------------------------------------------------------------
+constexpr uint32_t K3_MAX_K = 100;
+constexpr float K3_ERR_REL = 2.5e-4f;  // >= 3*2^-16 (dropped split terms) + fp32 accumulation over 3*dim terms
+constexpr float K3_ERR_REL_1PASS = 8.5e-3f;  // >= 2*2^-8 + 2^-16 (both operands rounded to bf16) + accumulation
+
+// passes the batch would run with: bf16x3 up to dim 384 (TMEM holds q_hi and q_lo), the single-pass
+// filter up to dim 768 (q_hi only) or when asked for (batch mode 3); 0 = K3 cannot serve this shape
+int k3_passes(const sema_index *s, uint32_t k)
+{
+    if (s->metric != SEMA_METRIC_COSINE || s->dim % k3::BLOCK_K != 0 || k > K3_MAX_K || s->planes_failed) return 0;
+    if (s->dim <= (uint32_t)k3::MAX_DIM) return s->batch_mode == 3 ? 1 : 3;
+    if (s->dim <= (uint32_t)k3::MAX_DIM_1PASS) return 1;
+    return 0;
+}
+
+// Bring the bf16 planes up to date with rows [0, n).  Tombstones invalidate from their row on.
+int k3_sync_planes(sema_index *s, uint64_t n)
+{
+    if (!s->planes) {
+        const uint64_t tiles = (s->capacity + k3::TILE_N - 1) / k3::TILE_N;
+        cudaError_t e = cudaMalloc(&s->planes, (size_t)(tiles ? tiles : 1) * k3::tile_bytes((int)s->dim));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            s->planes = nullptr;
+            s->planes_failed = true;  // not an error: the K2 loop serves the batch instead
+            return SEMA_ERR_NOMEM;
+        }
+        s->planes_rows = 0;
+    }
+    if (s->planes_rows >= n) return SEMA_OK;
+    const uint64_t begin = (s->planes_rows / k3::TILE_N) * k3::TILE_N;            // re-tile the partial last tile
+    const uint64_t end = ((n + k3::TILE_N - 1) / k3::TILE_N) * k3::TILE_N;
+    const uint64_t work = (end - begin) * (s->dim / 8);
+    uint64_t blocks = (work + 255) / 256;
+    if (blocks > (uint64_t)s->num_sms * 32) blocks = (uint64_t)s->num_sms * 32;
+    k3::split_planes_kernel<<<(unsigned)blocks, 256, 0, s->stream>>>(s->X, s->ld, s->dim, begin, end, n, s->planes);
+    CK(cudaGetLastError());
+    s->launches++;
+    s->planes_rows = n;
+    return SEMA_OK;
+}
+
+// q_ctas = CTAs along the query axis (each owns QT query tiles)
+template <int KC, int C, int PASSES, int QT>
+int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_ctas)
+{
+    auto kern = k3::batch_scan_kernel<KC, C, PASSES, QT>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[s->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC, PASSES, QT>::TOTAL));
+        attr_set[s->device & 63] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(q_ctas, p.parts, 1);
+    cfg.blockDim = dim3(k3::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = k3::Smem<KC, PASSES, QT>::TOTAL;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, p));
+    s->launches++;
+    return SEMA_OK;
+}
+
+// how many clusters of C CTAs of this kernel can be resident at once (cached per device)
+template <int KC, int C>
+int k3_max_clusters(sema_index *s, int *out)
+{
+    static int cached[64] = {0};
+    int &v = cached[s->device & 63];
+    if (v == 0) {
+        auto kern = k3::batch_scan_kernel<KC, C, 3, 1>;   // the single-pass kernels use no more shared memory
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k3::Smem<KC, 3>::TOTAL));
+        if (C == 1) {
+            v = s->num_sms;
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(C, (unsigned)s->num_sms, 1);
+            cfg.blockDim = dim3(k3::THREADS, 1, 1);
+            cfg.dynamicSmemBytes = k3::Smem<KC, 3>::TOTAL;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = C;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+            v = n > 0 ? n : 1;
+        }
+    }
+    *out = v;
+    return SEMA_OK;
+}
+
+template <int KC, int PASSES, int QT>
+int k3_launch_scan_p(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c)
+{
+    return c == 4 ? k3_launch_scan_c<KC, 4, PASSES, QT>(s, p, q_ctas)
+         : c == 2 ? k3_launch_scan_c<KC, 2, PASSES, QT>(s, p, q_ctas) : k3_launch_scan_c<KC, 1, PASSES, QT>(s, p, q_ctas);
+}
+template <int KC>
+int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c, int passes, int qt)
+{
+    if (passes == 3) return k3_launch_scan_p<KC, 3, 1>(s, p, q_ctas, c);
+    if constexpr (KC <= 64) {
+        if (qt == 2) return k3_launch_scan_p<KC, 1, 2>(s, p, q_ctas, c);
+    }
+    return k3_launch_scan_p<KC, 1, 1>(s, p, q_ctas, c);
+}
+template <int KC>
+int k3_clusters(sema_index *s, int c, int *out)
+{
+    return c == 4 ? k3_max_clusters<KC, 4>(s, out) : c == 2 ? k3_max_clusters<KC, 2>(s, out) : k3_max_clusters<KC, 1>(s, out);
+}
+
+// Qd: nq x dim dense on the device.  Results: device arrays [nq*k], [nq*k], [nq].
+int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+             uint32_t *nf_d)
+{
+    const uint32_t kc = k <= 16 ? 32 : (k <= 48 ? 64 : 128);
+    const int passes = k3_passes(s, k);
+    const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
+    const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
+    int rc;
+    // QT query tiles per CTA (2 in the single-pass mode when there are at least 2 tiles), clusters of
+    // csize CTAs along the query axis: the query-tile count is padded to a multiple of QT*csize
+    // (Qpad rows beyond nq are zero queries whose results are never read).
+    // (two tiles need 2*dim/2 + 128 TMEM columns and two candidate lists in shared memory)
+    const int qt_per_cta = (passes == 1 && q_tiles_all >= 2 && s->k3_qt != 1 && s->dim <= 384 && kc <= 64) ? 2 : 1;
+    const uint32_t q_ctas_all = (q_tiles_all + qt_per_cta - 1) / qt_per_cta;
+    // measured on 10M x 384 x 1024q: bf16x3 is fastest with clusters of 4 (128 SMs, higher clocks under the
+    // power cap), the single-pass filter with clusters of 2 (144 SMs; it is bound by L2->SM delivery)
+    const int cpref = passes == 1 ? 2 : 4;
+    const int csize = s->k3_cluster > 0 ? s->k3_cluster : (q_ctas_all >= (uint32_t)cpref ? cpref : (q_ctas_all >= 2 ? 2 : 1));
+    const uint32_t q_ctas_pad = ((q_ctas_all + csize - 1) / csize) * csize;
+    const size_t qpad_rows = (size_t)q_ctas_pad * qt_per_cta * k3::TILE_Q;
+    rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, qpad_rows * s->dim * sizeof(float));
+    if (rc) return rc;
+    if (s->flags_cap < nq) {
+        cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
+        s->flags_dev = nullptr; s->flags_pin = nullptr; s->flags_cap = 0;
+        CK(cudaMalloc(&s->flags_dev, (size_t)nq * sizeof(uint32_t)));
+        CK(cudaHostAlloc(&s->flags_pin, (size_t)nq * sizeof(uint32_t), cudaHostAllocPortable));
+        s->flags_cap = nq;
+    }
+    CK(cudaMemsetAsync(s->Qpad_dev, 0, qpad_rows * s->dim * sizeof(float), s->stream));
+    CK(cudaMemcpyAsync(s->Qpad_dev, Qd, (size_t)nq * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+
+    int max_clusters = 1;
+    rc = kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
+    if (rc) return rc;
+    const uint32_t groups_all = q_ctas_pad / csize;             // clusters along the query axis
+    // at most max_clusters cluster columns per launch; the clusters left over become row partitions
+    for (uint32_t g0 = 0; g0 < groups_all; g0 += (uint32_t)max_clusters) {
+        const uint32_t groups = (groups_all - g0) < (uint32_t)max_clusters ? (groups_all - g0) : (uint32_t)max_clusters;
+        const uint32_t q_ctas = groups * csize;                 // CTAs along the query axis in this launch
+        const uint32_t qt0 = g0 * csize * qt_per_cta;           // first query tile of this launch
+        const uint32_t q_tiles = q_ctas * qt_per_cta;
+        uint32_t parts = (uint32_t)max_clusters / groups;
+        if (parts > n_tiles) parts = n_tiles;
+        if (parts < 1) parts = 1;
+        const size_t nqp = (size_t)q_tiles * k3::TILE_Q;
+        rc = ensure(reinterpret_cast<void **>(&s->cand_rows), &s->cand_cap, nqp * parts * kc * sizeof(uint32_t));
+        if (rc) return rc;
+        rc = ensure(reinterpret_cast<void **>(&s->cand_thr), &s->thr_cap, nqp * parts * sizeof(float));
+        if (rc) return rc;
+        k3::Params p;
+        p.planes = s->planes;
+        p.Q = s->Qpad_dev + (size_t)qt0 * k3::TILE_Q * s->dim;
+        p.cand_rows = s->cand_rows;
+        p.cand_thr = s->cand_thr;
+        p.n_rows = n;
+        p.n_tiles = n_tiles;
+        p.parts = parts;
+        p.dim = s->dim;
+        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, csize, passes, qt_per_cta)
+                      : k3_launch_scan<128>(s, p, q_ctas, csize, passes, qt_per_cta);
+        if (rc) return rc;
+        const uint32_t q_first = qt0 * k3::TILE_Q;
+        if (q_first >= nq) break;
+        const uint32_t q_cnt = (nq - q_first) < (uint32_t)nqp ? (nq - q_first) : (uint32_t)nqp;
+        k3::RescoreParams r;
+        r.X = reinterpret_cast<const float4 *>(s->X);
+        r.Q = p.Q;
+        r.cand_rows = s->cand_rows;
+        r.cand_thr = s->cand_thr;
+        r.res_ids = ids_d + (size_t)q_first * k;
+        r.res_scores = sc_d + (size_t)q_first * k;
+        r.res_nfound = nf_d + q_first;
+        r.flags = s->flags_dev + q_first;
+        r.ld4 = s->ld / 4;
+        r.dim = s->dim;
+        r.k = k;
+        r.parts = parts;
+        r.kc = kc;
+        r.row_base = s->row_base;
+        r.max_norm2 = s->max_norm2;
+        r.err_rel = passes == 1 ? K3_ERR_REL_1PASS : K3_ERR_REL;
+        if (k <= 32) k3::rescore_kernel<1><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        else if (k <= 64) k3::rescore_kernel<2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        else k3::rescore_kernel<4><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        CK(cudaGetLastError());
+        s->launches++;
+    }
+    // queries whose exactness could not be proven (heavy ties / near-duplicates) go through K2
+    CK(cudaMemcpyAsync(s->flags_pin, s->flags_dev, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->k3_queries += nq;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (!s->flags_pin[i]) continue;
+        s->k3_fallbacks++;
+        rc = scan_query(s, s->Qpad_dev + (size_t)i * s->dim, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i);
+        if (rc) return rc;
+    }
+    return SEMA_OK;
+}
+
+}  // namespace
+
+namespace sema_impl {
+
+// Batched search with the queries already on the device (nq x dim dense).
+int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+               uint32_t *nf_d)
+{
+    const bool want_k3 = s->batch_mode >= 2 || (s->batch_mode == 0 && nq >= 4);
+    if (want_k3 && k3_passes(s, k) != 0) {
+        int rc = k3_sync_planes(s, n);
+        if (rc == SEMA_OK) return k3_batch(s, Qd, nq, n, k, ids_d, sc_d, nf_d);
+        if (rc != SEMA_ERR_NOMEM) return rc;
+    }
+    // K2 once per query (still one HBM pass per query)
+    const float *Qp = Qd;
+    if (s->ld != s->dim) {
+        int rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, (size_t)nq * s->ld * sizeof(float));
+        if (rc) return rc;
+        CK(cudaMemsetAsync(s->Qpad_dev, 0, (size_t)nq * s->ld * sizeof(float), s->stream));
+        CK(cudaMemcpy2DAsync(s->Qpad_dev, s->ld * sizeof(float), Qd, s->dim * sizeof(float), s->dim * sizeof(float),
+                             nq, cudaMemcpyDeviceToDevice, s->stream));
+        Qp = s->Qpad_dev;
+    }
+    for (uint32_t i = 0; i < nq; ++i) {
+        int rc = scan_query(s, Qp + (size_t)i * s->ld, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i);
+        if (rc) return rc;
+    }
+    return SEMA_OK;
+}
+
+}  // namespace sema_impl
+
+extern "C" {
+
+int sema_index_search_batch(sema_index *s, const float *Q, uint32_t nq, uint32_t k,
+                            uint64_t *row_ids, float *scores, uint32_t *n_found)
+{
+    if (!s || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
+    if (nq && !Q) return fail(SEMA_ERR_INVALID, "null queries");
+    if (k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u > SEMA_MAX_K %u", k, SEMA_MAX_K);
+    if (k && nq && (!row_ids || !scores)) return fail(SEMA_ERR_INVALID, "null output");
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    for (uint32_t i = 0; i < nq; ++i) n_found[i] = 0;
+    if (k == 0 || n == 0 || nq == 0) return SEMA_OK;
+    rc = ensure(reinterpret_cast<void **>(&s->Q_dev), &s->batch_cap_q, (size_t)nq * s->dim * sizeof(float));
+    if (rc) return rc;
+    if (s->batch_cap_res < (size_t)nq * k) {
+        cudaFree(s->bids_dev); cudaFree(s->bsc_dev); cudaFree(s->bnf_dev);
+        s->bids_dev = nullptr; s->bsc_dev = nullptr; s->bnf_dev = nullptr; s->batch_cap_res = 0;
+        CK(cudaMalloc(&s->bids_dev, (size_t)nq * k * sizeof(uint64_t)));
+        CK(cudaMalloc(&s->bsc_dev, (size_t)nq * k * sizeof(float)));
+        CK(cudaMalloc(&s->bnf_dev, (size_t)nq * sizeof(uint32_t)));
+        s->batch_cap_res = (size_t)nq * k;
+    }
+    CK(cudaMemcpyAsync(s->Q_dev, Q, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (s->normalize_queries) {
+        rc = normalize_queries_dev(s, s->Q_dev, s->dim, nq);
+        if (rc) return rc;
+    }
+    rc = batch_core(s, s->Q_dev, nq, (uint32_t)n, k, s->bids_dev, s->bsc_dev, s->bnf_dev);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(row_ids, s->bids_dev, (size_t)nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(scores, s->bsc_dev, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(n_found, s->bnf_dev, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return SEMA_OK;
+}
+
+int sema_index_search_batch_device(sema_index *s, const float *Q_dev, uint32_t nq, uint32_t k,
+                                   uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !Q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K || nq == 0) return fail(SEMA_ERR_INVALID, "k %u / nq %u out of range", k, nq);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(n_found_dev, 0, (size_t)nq * sizeof(uint32_t), s->stream));
+        return SEMA_OK;
+    }
+    return batch_core(s, Q_dev, nq, (uint32_t)n, k, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_index_set_batch_mode(sema_index *s, int mode)
+{
+    if (!s) return -1;
+    if (mode >= 0 && mode <= 3) s->batch_mode = mode;
+    return s->batch_mode;
+}
+
+int sema_index_batch_stats(const sema_index *s, uint64_t *k3_queries, uint64_t *k3_fallbacks)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (k3_queries) *k3_queries = s->k3_queries;
+    if (k3_fallbacks) *k3_fallbacks = s->k3_fallbacks;
+    return SEMA_OK;
+}
+
+}  // extern "C"

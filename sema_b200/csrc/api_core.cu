@@ -1,0 +1,536 @@
+// api_core.cu — lifecycle, ingest (K1), tombstones, compaction, disk cache, properties.
+#include "index_impl.cuh"
+#include "k1_ingest.cuh"
+
+using namespace sema;
+using namespace sema_impl;
+
+namespace sema_impl {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int poll_ingest(sema_index *s, bool wait)
+{
+    while (!s->pending.empty()) {
+        Pending &p = s->pending.front();
+        cudaError_t e = wait ? cudaEventSynchronize(p.ev) : cudaEventQuery(p.ev);
+        if (e == cudaErrorNotReady) break;
+        if (e != cudaSuccess) return fail(SEMA_ERR_CUDA, "ingest event: %s", cudaGetErrorString(e));
+        s->n_visible = p.rows_after;
+        cudaEventDestroy(p.ev);
+        s->pending.pop_front();
+    }
+    return SEMA_OK;
+}
+
+int ensure(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return SEMA_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CK(cudaMalloc(p, need));
+    *cap = need;
+    return SEMA_OK;
+}
+
+// K1 on query vectors in place (nq rows of `stride` floats on the device, on the query stream)
+int normalize_queries_dev(sema_index *s, float *q, uint64_t stride, uint32_t nq)
+{
+    for (uint32_t done = 0; done < nq; done += 65536) {
+        const uint32_t m = (nq - done) < 65536u ? (nq - done) : 65536u;
+        uint64_t blocks = ((uint64_t)m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+        if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
+        float *base = q + (size_t)done * stride;
+        // generic (scalar) kernel: src == dst, same stride; pad columns [dim, stride) are rewritten as zeros
+        ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(
+            base, stride, base, (uint32_t)stride, s->dim, m, nullptr, s->qscratch,
+            1, reinterpret_cast<float *>(s->qscratch + 65536));
+        CK(cudaGetLastError());
+        s->launches++;
+    }
+    return SEMA_OK;
+}
+
+}  // namespace sema_impl
+
+namespace {
+
+int launch_ingest(sema_index *s, const float *src, uint64_t src_ld, uint64_t first, uint64_t n,
+                  const uint8_t *valid_in, int normalize, bool vec4)
+{
+    float *dst = s->X + first * s->ld;
+    uint64_t warps_needed = n;
+    uint64_t blocks = (warps_needed * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+    const uint64_t maxb = (uint64_t)s->num_sms * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    if (vec4)
+        ingest_kernel<true><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
+            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize, s->max_norm2);
+    else
+        ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
+            src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize, s->max_norm2);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+int publish(sema_index *s, uint64_t n)
+{
+    s->n_rows += n;
+    Pending p;
+    CK(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(p.ev, s->ingest_stream));
+    p.rows_after = s->n_rows;
+    s->pending.push_back(p);
+    return SEMA_OK;
+}
+
+
+int check_append(sema_index *s, uint64_t n)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (s->n_rows + n > s->capacity)
+        return fail(SEMA_ERR_CAPACITY, "append of %llu rows exceeds capacity %llu (size %llu)",
+                    (unsigned long long)n, (unsigned long long)s->capacity, (unsigned long long)s->n_rows);
+    if ((uint64_t)s->row_base + s->n_rows + n > 0xfffffffeull)
+        return fail(SEMA_ERR_CAPACITY, "global row ids must stay below 2^32-1");
+    return SEMA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sema_last_error(void) { return g_err; }
+const char *sema_version(void) { return "sema_b200 0.1 (sm_100a)"; }
+
+int sema_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int sema_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return fail(SEMA_ERR_INVALID, "null out");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return SEMA_OK;
+}
+
+int sema_host_free(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return SEMA_OK;
+}
+
+int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metric, sema_index **out)
+{
+    if (!out) return fail(SEMA_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (dim == 0 || dim > SEMA_MAX_DIM) return fail(SEMA_ERR_INVALID, "dim %u outside [1, %u]", dim, SEMA_MAX_DIM);
+    if (metric != SEMA_METRIC_COSINE && metric != SEMA_METRIC_L2) return fail(SEMA_ERR_INVALID, "unknown metric %d", metric);
+    if (capacity_rows > 0xfffffffeull) return fail(SEMA_ERR_INVALID, "capacity_rows must be < 2^32-1");
+    int ndev = sema_device_count();
+    if (ndev == 0) return fail(SEMA_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(SEMA_ERR_INVALID, "device %d outside [0, %d)", device, ndev);
+    CK(cudaSetDevice(device));
+    sema_index *s = new (std::nothrow) sema_index();
+    if (!s) return fail(SEMA_ERR_NOMEM, "host allocation failed");
+    s->device = device;
+    s->dim = dim;
+    s->ld = (dim + 3u) & ~3u;
+    s->capacity = capacity_rows;
+    s->metric = metric;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete s; return fail(SEMA_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    s->num_sms = prop.multiProcessorCount;
+    const size_t xbytes = (size_t)(capacity_rows ? capacity_rows : 1) * s->ld * sizeof(float);
+    const size_t res_bytes = 8 + (size_t)SEMA_MAX_K * 12;
+#define CKD(call)                                                                           \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            int code_ = e_ == cudaErrorMemoryAllocation ? SEMA_ERR_NOMEM : SEMA_ERR_CUDA;   \
+            fail(code_, "%s failed: %s", #call, cudaGetErrorString(e_));                    \
+            cudaGetLastError();                                                             \
+            sema_index_destroy(s);                                                          \
+            return code_;                                                                   \
+        }                                                                                   \
+    } while (0)
+    CKD(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    CKD(cudaStreamCreateWithFlags(&s->ingest_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    CKD(cudaMalloc(&s->X, xbytes));
+    CKD(cudaMalloc(&s->valid, capacity_rows ? capacity_rows : 1));
+    CKD(cudaMalloc(&s->q_dev, s->ld * sizeof(float)));
+    CKD(cudaMemset(s->q_dev, 0, s->ld * sizeof(float)));
+    CKD(cudaHostAlloc(&s->q_pin, s->ld * sizeof(float), cudaHostAllocPortable));
+    memset(s->q_pin, 0, s->ld * sizeof(float));
+    CKD(cudaMalloc(&s->partials, (size_t)s->num_sms * MAX_BLOCKS_PER_SM * K_PASS * sizeof(uint64_t)));
+    CKD(cudaMalloc(&s->ticket, 2 * sizeof(unsigned int)));
+    CKD(cudaMemset(s->ticket, 0, 2 * sizeof(unsigned int)));
+    CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
+    CKD(cudaMalloc(&s->max_norm2, sizeof(float)));
+    CKD(cudaMalloc(&s->qscratch, 65536 + 16));
+    CKD(cudaMemset(s->max_norm2, 0, sizeof(float)));
+    CKD(cudaMalloc(&s->res_dev, res_bytes));
+    CKD(cudaHostAlloc(&s->res_pin, res_bytes, cudaHostAllocPortable));
+    CKD(cudaDeviceSynchronize());
+#undef CKD
+    *out = s;
+    return SEMA_OK;
+}
+
+int sema_index_destroy(sema_index *s)
+{
+    if (!s) return SEMA_OK;
+    cudaSetDevice(s->device);
+    if (s->own_stream) cudaStreamSynchronize(s->own_stream);
+    if (s->ingest_stream) cudaStreamSynchronize(s->ingest_stream);
+    for (auto &p : s->pending) cudaEventDestroy(p.ev);
+    cudaFree(s->X); cudaFree(s->valid); cudaFree(s->q_dev); cudaFreeHost(s->q_pin);
+    cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->keys_dev); cudaFree(s->res_dev);
+    cudaFreeHost(s->res_pin); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
+    cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
+    cudaFree(s->qscratch); cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
+    cudaFree(s->cand_thr); cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->ingest_stream) cudaStreamDestroy(s->ingest_stream);
+    cudaGetLastError();
+    delete s;
+    return SEMA_OK;
+}
+
+int sema_index_append_async(sema_index *s, const float *rows, uint64_t n, const uint8_t *valid,
+                            int normalize, uint64_t *first_row)
+{
+    int rc = check_append(s, n);
+    if (rc) return rc;
+    if (n && !rows) return fail(SEMA_ERR_INVALID, "null rows");
+    CK(cudaSetDevice(s->device));
+    const uint64_t first = s->n_rows;
+    if (first_row) *first_row = first;
+    if (n == 0) return SEMA_OK;
+    float *dst = s->X + first * s->ld;
+    // host rows land directly in their final place; K1 then normalises in place
+    if (s->ld == s->dim)
+        CK(cudaMemcpyAsync(dst, rows, n * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->ingest_stream));
+    else
+        CK(cudaMemcpy2DAsync(dst, s->ld * sizeof(float), rows, s->dim * sizeof(float),
+                             s->dim * sizeof(float), n, cudaMemcpyHostToDevice, s->ingest_stream));
+    const uint8_t *vin = nullptr;
+    if (valid) {
+        CK(cudaMemcpyAsync(s->valid + first, valid, n, cudaMemcpyHostToDevice, s->ingest_stream));
+        vin = s->valid + first;
+    }
+    rc = launch_ingest(s, dst, s->ld, first, n, vin, normalize, s->ld == s->dim);
+    if (rc) return rc;
+    return publish(s, n);
+}
+
+int sema_index_flush(sema_index *s)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->ingest_stream));
+    return poll_ingest(s, true);
+}
+
+int sema_index_append(sema_index *s, const float *rows, uint64_t n, const uint8_t *valid,
+                      int normalize, uint64_t *first_row)
+{
+    int rc = sema_index_append_async(s, rows, n, valid, normalize, first_row);
+    if (rc) return rc;
+    return sema_index_flush(s);
+}
+
+int sema_index_append_device(sema_index *s, const float *rows_dev, uint64_t n,
+                             const uint8_t *valid_dev, int normalize, uint64_t *first_row)
+{
+    int rc = check_append(s, n);
+    if (rc) return rc;
+    if (n && !rows_dev) return fail(SEMA_ERR_INVALID, "null rows");
+    CK(cudaSetDevice(s->device));
+    const uint64_t first = s->n_rows;
+    if (first_row) *first_row = first;
+    if (n == 0) return SEMA_OK;
+    const bool vec4 = s->ld == s->dim && (reinterpret_cast<uintptr_t>(rows_dev) & 15) == 0;
+    rc = launch_ingest(s, rows_dev, s->dim, first, n, valid_dev, normalize, vec4);
+    if (rc) return rc;
+    rc = publish(s, n);
+    if (rc) return rc;
+    return sema_index_flush(s);
+}
+
+int sema_index_append_synthetic(sema_index *s, uint64_t seed, uint64_t synth_row0, uint64_t n,
+                                int normalize, uint64_t *first_row)
+{
+    int rc = check_append(s, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(s->device));
+    const uint64_t first = s->n_rows;
+    if (first_row) *first_row = first;
+    if (n == 0) return SEMA_OK;
+    float *dst = s->X + first * s->ld;
+    synth_kernel<<<s->num_sms * 16, INGEST_THREADS, 0, s->ingest_stream>>>(dst, s->ld, s->dim, seed, synth_row0, n);
+    CK(cudaGetLastError());
+    s->launches++;
+    rc = launch_ingest(s, dst, s->ld, first, n, nullptr, normalize, s->ld == s->dim);
+    if (rc) return rc;
+    rc = publish(s, n);
+    if (rc) return rc;
+    return sema_index_flush(s);
+}
+
+int sema_index_tombstone(sema_index *s, const uint64_t *rows, uint64_t n)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (n && !rows) return fail(SEMA_ERR_INVALID, "null rows");
+    if (n == 0) return SEMA_OK;
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < n; ++i)
+        if (rows[i] >= s->n_rows)
+            return fail(SEMA_ERR_INVALID, "tombstone row %llu >= size %llu", (unsigned long long)rows[i], (unsigned long long)s->n_rows);
+    rc = ensure(reinterpret_cast<void **>(&s->tomb_dev), &s->tomb_cap, n * sizeof(uint64_t));
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s->tomb_dev, rows, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    uint64_t blocks = (n * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+    if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
+    tombstone_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, s->tomb_dev, n, s->n_rows, s->valid);
+    CK(cudaGetLastError());
+    s->launches++;
+    CK(cudaStreamSynchronize(s->stream));
+    // the bf16 planes of K3 must forget the dead rows: re-tile from the first one on
+    uint64_t lowest = s->planes_rows;
+    for (uint64_t i = 0; i < n; ++i) if (rows[i] < lowest) lowest = rows[i];
+    s->planes_rows = lowest;
+    return SEMA_OK;
+}
+
+
+int sema_index_compact(sema_index *s, uint64_t *new_row_of_old, uint64_t *n_live_out)
+{
+    return sema_index_compact_keep(s, nullptr, new_row_of_old, n_live_out);
+}
+
+int sema_index_compact_keep(sema_index *s, const uint8_t *keep, uint64_t *new_row_of_old, uint64_t *n_live_out)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    const uint64_t n = s->n_rows;
+    std::vector<uint8_t> valid(n ? n : 1);
+    if (n) CK(cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> src;   // src[new] = old, ascending
+    std::vector<uint8_t> new_valid;
+    src.reserve(n);
+    new_valid.reserve(n);
+    for (uint64_t r = 0; r < n; ++r) {
+        if (keep ? keep[r] != 0 : valid[r] != 0) {
+            new_valid.push_back(valid[r]);
+            if (new_row_of_old) new_row_of_old[r] = src.size();
+            src.push_back((uint32_t)r);
+        } else if (new_row_of_old) {
+            new_row_of_old[r] = ~0ull;
+        }
+    }
+    const uint64_t live = src.size();
+    if (n_live_out) *n_live_out = live;
+    if (live == n) return SEMA_OK;  // nothing to drop
+    // gather through a bounce buffer, chunk by chunk in ascending order: a chunk's destination
+    // [j*C, (j+1)*C) never overlaps a later chunk's sources (src[i] >= i)
+    const uint64_t C = 1u << 16;
+    float *tmp = nullptr;
+    uint32_t *src_dev = nullptr;
+    cudaError_t e = cudaMalloc(&tmp, C * s->ld * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&src_dev, C * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        cudaFree(tmp); cudaFree(src_dev); cudaGetLastError();
+        return fail(SEMA_ERR_NOMEM, "compaction scratch: %s", cudaGetErrorString(e));
+    }
+    uint64_t first_moved = 0;
+    while (first_moved < live && src[first_moved] == first_moved) ++first_moved;   // untouched prefix
+    for (uint64_t at = first_moved; at < live; at += C) {
+        const uint64_t m = (live - at) < C ? (live - at) : C;
+        CK(cudaMemcpyAsync(src_dev, src.data() + at, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        uint64_t blocks = (m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
+        if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
+        gather_rows_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, src_dev, m, tmp);
+        CK(cudaGetLastError());
+        s->launches++;
+        CK(cudaMemcpyAsync(s->X + at * s->ld, tmp, m * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));   // src_dev / tmp are reused by the next chunk
+    }
+    if (live) CK(cudaMemcpyAsync(s->valid, new_valid.data(), live, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(tmp);
+    cudaFree(src_dev);
+    s->n_rows = live;
+    s->n_visible = live;
+    if (s->planes_rows > first_moved) s->planes_rows = first_moved;   // K3 planes: re-tile from the first moved row
+    return SEMA_OK;
+}
+
+namespace {
+struct SemaFileHeader {
+    char magic[8];
+    uint32_t dim;
+    int32_t metric;
+    uint64_t n_rows;
+    unsigned char pad[40];
+};
+static_assert(sizeof(SemaFileHeader) == 64, "header is 64 bytes");
+}  // namespace
+
+int sema_index_save(sema_index *s, const char *path)
+{
+    if (!s || !path) return fail(SEMA_ERR_INVALID, "null argument");
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(SEMA_ERR_INVALID, "cannot open %s for writing", path);
+    SemaFileHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "SEMAIDX1", 8);
+    h.dim = s->dim;
+    h.metric = s->metric;
+    h.n_rows = s->n_rows;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    const uint64_t n = s->n_rows;
+    std::vector<uint8_t> valid(n ? n : 1);
+    if (ok && n) {
+        cudaError_t e = cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost);
+        ok = e == cudaSuccess && fwrite(valid.data(), 1, n, f) == n;
+    }
+    const uint64_t C = 1u << 16;
+    float *pin = nullptr;
+    if (ok && n) ok = cudaHostAlloc(&pin, C * s->dim * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+    for (uint64_t at = 0; ok && at < n; at += C) {
+        const uint64_t m = (n - at) < C ? (n - at) : C;
+        cudaError_t e = cudaMemcpy2D(pin, s->dim * sizeof(float), s->X + at * s->ld, s->ld * sizeof(float),
+                                     s->dim * sizeof(float), m, cudaMemcpyDeviceToHost);
+        ok = e == cudaSuccess && fwrite(pin, sizeof(float), m * s->dim, f) == m * s->dim;
+    }
+    if (pin) cudaFreeHost(pin);
+    ok = (fclose(f) == 0) && ok;
+    cudaGetLastError();
+    return ok ? SEMA_OK : fail(SEMA_ERR_CUDA, "writing %s failed", path);
+}
+
+int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_index **out)
+{
+    if (!path || !out) return fail(SEMA_ERR_INVALID, "null argument");
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(SEMA_ERR_INVALID, "cannot open %s", path);
+    SemaFileHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SEMAIDX1", 8) != 0) {
+        fclose(f);
+        return fail(SEMA_ERR_INVALID, "%s is not a sema index file", path);
+    }
+    if (capacity_rows < h.n_rows) capacity_rows = h.n_rows;
+    sema_index *s = nullptr;
+    int rc = sema_index_create(device, h.dim, capacity_rows, h.metric, &s);
+    if (rc) { fclose(f); return rc; }
+    const uint64_t n = h.n_rows, C = 1u << 16;
+    std::vector<uint8_t> valid(n ? n : 1);
+    bool ok = n == 0 || fread(valid.data(), 1, n, f) == n;
+    float *pin = nullptr;
+    if (ok && n) ok = cudaHostAlloc(&pin, C * h.dim * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+    for (uint64_t at = 0; ok && at < n; at += C) {
+        const uint64_t m = (n - at) < C ? (n - at) : C;
+        ok = fread(pin, sizeof(float), m * h.dim, f) == m * h.dim;
+        if (ok) {
+            rc = sema_index_append(s, pin, m, valid.data() + at, /*normalize=*/0, nullptr);   // rows are stored normalised
+            ok = rc == SEMA_OK;
+        }
+    }
+    if (pin) cudaFreeHost(pin);
+    fclose(f);
+    if (!ok) {
+        sema_index_destroy(s);
+        return rc ? rc : fail(SEMA_ERR_INVALID, "%s is truncated", path);
+    }
+    *out = s;
+    return SEMA_OK;
+}
+
+int sema_index_set_normalize_queries(sema_index *s, int on)
+{
+    if (!s) return -1;
+    if (on >= 0) s->normalize_queries = on ? 1 : 0;
+    return s->normalize_queries;
+}
+
+int sema_index_set_row_base(sema_index *s, uint64_t row_base)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (row_base + s->capacity > 0xfffffffeull) return fail(SEMA_ERR_INVALID, "row_base + capacity must be < 2^32-1");
+    s->row_base = (uint32_t)row_base;
+    return SEMA_OK;
+}
+
+int sema_index_set_stream(sema_index *s, void *cuda_stream, int external)
+{
+    if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    s->stream = external ? reinterpret_cast<cudaStream_t>(cuda_stream) : s->own_stream;
+    return SEMA_OK;
+}
+
+uint64_t sema_index_size(const sema_index *s) { return s ? s->n_rows : 0; }
+uint64_t sema_index_visible(sema_index *s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    poll_ingest(s, false);
+    return s->n_visible;
+}
+uint64_t sema_index_capacity(const sema_index *s) { return s ? s->capacity : 0; }
+uint32_t sema_index_dim(const sema_index *s) { return s ? s->dim : 0; }
+int sema_index_device(const sema_index *s) { return s ? s->device : -1; }
+uint64_t sema_index_last_snapshot(const sema_index *s) { return s ? s->last_snapshot : 0; }
+uint64_t sema_index_launch_count(const sema_index *s) { return s ? s->launches : 0; }
+
+int sema_index_set_scan_variant(sema_index *s, int variant)
+{
+    if (!s) return -1;
+    if (variant >= 200) { s->k3_qt = variant - 200; return variant; }        // 200 = auto, 201 = one query tile per CTA
+    if (variant >= 100) { s->k3_cluster = variant - 100; return variant; }   // 100 = auto, 101/102/104 = K3 cluster size
+    if (variant >= 0) s->variant = variant;
+    return s->variant;
+}
+
+int sema_index_read_rows(sema_index *s, uint64_t first_row, uint64_t n, float *out)
+{
+    if (!s || (n && !out)) return fail(SEMA_ERR_INVALID, "null argument");
+    int rc = sema_index_flush(s);
+    if (rc) return rc;
+    if (first_row + n > s->n_rows) return fail(SEMA_ERR_INVALID, "rows [%llu, %llu) outside size %llu",
+                                               (unsigned long long)first_row, (unsigned long long)(first_row + n), (unsigned long long)s->n_rows);
+    if (n == 0) return SEMA_OK;
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpy2D(out, s->dim * sizeof(float), s->X + first_row * s->ld, s->ld * sizeof(float),
+                    s->dim * sizeof(float), n, cudaMemcpyDeviceToHost));
+    return SEMA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+// api_search.cu — K2 (scan + fused top-k) and K4 (merge) dispatch; single-query entry points.
+#include "index_impl.cuh"
+#include "k2_scan.cuh"
+#include "k4_merge.cuh"
+
+using namespace sema;
+using namespace sema_impl;
+
+namespace {
+
+// ---- K2 dispatch ---------------------------------------------------------------
+struct ScanArgs {
+    const float *q_dev;
+    uint32_t n, k;
+    const uint64_t *bound;
+    uint64_t *out_keys;
+    uint64_t *res_ids;
+    float *res_scores;
+    uint32_t *res_nfound;
+    const Exchange *x = nullptr;   // sharded mode: fused peer exchange (single pass only)
+};
+
+template <int NV, int R, int M, int METRIC>
+int run_scan(sema_index *s, const ScanArgs &a)
+{
+    auto kern = scan_topk_kernel<NV, R, M, METRIC>;
+    static int occ[64] = {0};  // per device
+    const size_t dyn = NV > 0 ? 0 : (size_t)s->ld * sizeof(float);
+    int &o = occ[s->device & 63];
+    if (o == 0 || NV == 0) {
+        int t = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t, kern, SCAN_THREADS, dyn));
+        if (t < 1) return fail(SEMA_ERR_UNSUPPORTED, "scan kernel does not fit on an SM");
+        o = t > MAX_BLOCKS_PER_SM ? MAX_BLOCKS_PER_SM : t;
+    }
+    const uint32_t nb = (a.n + R - 1) / R;
+    uint32_t grid = (uint32_t)(s->num_sms * o);
+    const uint32_t need = (nb + SCAN_WARPS - 1) / SCAN_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    ScanParams p;
+    p.X = reinterpret_cast<const float4 *>(s->X);
+    p.q = a.q_dev;
+    p.partials = s->partials;
+    p.ticket = s->ticket;
+    p.bound = a.bound;
+    p.out_keys = a.out_keys;
+    p.res_ids = a.res_ids;
+    p.res_scores = a.res_scores;
+    p.res_nfound = a.res_nfound;
+    p.n = a.n;
+    p.ld4 = s->ld / 4;
+    p.k = a.k;
+    p.row_base = s->row_base;
+    if (a.x) p.x = *a.x;
+    else memset(&p.x, 0, sizeof p.x);
+    kern<<<grid, SCAN_THREADS, dyn, s->stream>>>(p);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+template <int NV, int R, int METRIC>
+int scan_m(sema_index *s, const ScanArgs &a)
+{
+    if (a.k <= 32) return run_scan<NV, R, 1, METRIC>(s, a);
+    if (a.k <= 64) return run_scan<NV, R, 2, METRIC>(s, a);
+    return run_scan<NV, R, 4, METRIC>(s, a);
+}
+
+template <int METRIC>
+int scan_shape(sema_index *s, const ScanArgs &a)
+{
+    const uint32_t ld4 = s->ld / 4;
+    if (ld4 == 96) {
+        switch (s->variant) {
+            case 1: return scan_m<3, 4, METRIC>(s, a);
+            case 2: return scan_m<3, 2, METRIC>(s, a);
+            default: return scan_m<3, 8, METRIC>(s, a);   // R = 8: best or tied on every box measured
+        }
+    }
+    if (ld4 == 192) {
+        switch (s->variant) {
+            case 1: return scan_m<6, 4, METRIC>(s, a);
+            default: return scan_m<6, 2, METRIC>(s, a);   // 24 float4 per lane per 4 rows is too many registers
+        }
+    }
+    return scan_m<0, 4, METRIC>(s, a);
+}
+
+// one fused pass (k <= K_PASS)
+int scan_pass(sema_index *s, const ScanArgs &a)
+{
+    return s->metric == SEMA_METRIC_L2 ? scan_shape<METRIC_L2>(s, a) : scan_shape<METRIC_COSINE>(s, a);
+}
+
+template <int METRIC>
+int merge_pass_m(sema_index *s, const uint64_t *keys, uint32_t total, uint32_t k,
+                 const uint64_t *bound, uint64_t *out_keys, uint64_t *ids, float *sc, uint32_t *nf)
+{
+    if (k <= 32)
+        merge_topk_kernel<1, METRIC><<<1, MERGE_THREADS, 0, s->stream>>>(keys, total, (int)k, bound, out_keys, ids, sc, nf);
+    else if (k <= 64)
+        merge_topk_kernel<2, METRIC><<<1, MERGE_THREADS, 0, s->stream>>>(keys, total, (int)k, bound, out_keys, ids, sc, nf);
+    else
+        merge_topk_kernel<4, METRIC><<<1, MERGE_THREADS, 0, s->stream>>>(keys, total, (int)k, bound, out_keys, ids, sc, nf);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+int decode(sema_index *s, const uint64_t *keys, uint32_t k, uint64_t *ids, float *sc, uint32_t *nf)
+{
+    if (s->metric == SEMA_METRIC_L2)
+        decode_kernel<METRIC_L2><<<1, 256, 0, s->stream>>>(keys, (int)k, ids, sc, nf);
+    else
+        decode_kernel<METRIC_COSINE><<<1, 256, 0, s->stream>>>(keys, (int)k, ids, sc, nf);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+// Full selection of the best k (any k <= SEMA_MAX_K) for one query that is already on
+// the device.  Exactly one of {out_keys} / {res_*} may be null.
+}  // namespace
+
+namespace sema_impl {
+
+int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys,
+               uint64_t *res_ids, float *res_scores, uint32_t *res_nfound, const Exchange *x)
+{
+    if (k <= K_PASS) {
+        ScanArgs a{q_dev, n, k, nullptr, out_keys ? out_keys : s->keys_dev, res_ids, res_scores, res_nfound, x};
+        return scan_pass(s, a);
+    }
+    if (x) return fail(SEMA_ERR_UNSUPPORTED, "the fused shard exchange covers k <= %d", K_PASS);
+    uint64_t *keys = out_keys ? out_keys : s->keys_dev;
+    for (uint32_t done = 0; done < k; done += K_PASS) {
+        const uint32_t kp = (k - done) < (uint32_t)K_PASS ? (k - done) : (uint32_t)K_PASS;
+        ScanArgs a{q_dev, n, kp, done ? keys + done - 1 : nullptr, keys + done, nullptr, nullptr, nullptr};
+        int rc = scan_pass(s, a);
+        if (rc) return rc;
+    }
+    if (res_ids) return decode(s, keys, k, res_ids, res_scores, res_nfound);
+    return SEMA_OK;
+}
+
+}  // namespace sema_impl
+
+extern "C" {
+
+int sema_index_search(sema_index *s, const float *q, uint32_t k, uint64_t *row_ids, float *scores,
+                      uint32_t *n_found)
+{
+    if (!s || !q || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u > SEMA_MAX_K %u", k, SEMA_MAX_K);
+    if (k && (!row_ids || !scores)) return fail(SEMA_ERR_INVALID, "null output");
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    *n_found = 0;
+    if (k == 0 || n == 0) return SEMA_OK;
+    memcpy(s->q_pin, q, s->dim * sizeof(float));
+    CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (s->normalize_queries) {
+        rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
+        if (rc) return rc;
+    }
+    uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
+    float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
+    rc = scan_query(s, s->q_dev, (uint32_t)n, k, nullptr, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev));
+    if (rc) return rc;
+    const size_t bytes = 8 + 12 * (size_t)k;
+    CK(cudaMemcpyAsync(s->res_pin, s->res_dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const uint32_t nf = *reinterpret_cast<uint32_t *>(s->res_pin);
+    *n_found = nf;
+    memcpy(row_ids, s->res_pin + 8, nf * sizeof(uint64_t));
+    memcpy(scores, s->res_pin + 8 + 8 * (size_t)k, nf * sizeof(float));
+    return SEMA_OK;
+}
+
+int sema_index_search_keys_device(sema_index *s, const float *q_dev, uint32_t k, uint64_t *keys_dev)
+{
+    if (!s || !q_dev || !keys_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u outside [1, %u]", k, SEMA_MAX_K);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(keys_dev, 0, k * sizeof(uint64_t), s->stream));
+        return SEMA_OK;
+    }
+    const float *qd = q_dev;
+    if (s->ld != s->dim || (reinterpret_cast<uintptr_t>(q_dev) & 15)) {
+        CK(cudaMemcpyAsync(s->q_dev, q_dev, s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        qd = s->q_dev;
+    }
+    return scan_query(s, qd, (uint32_t)n, k, keys_dev, nullptr, nullptr, nullptr);
+}
+
+int sema_index_search_device(sema_index *s, const float *q_dev, uint32_t k, uint64_t *ids_dev,
+                             float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u outside [1, %u]", k, SEMA_MAX_K);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(n_found_dev, 0, sizeof(uint32_t), s->stream));
+        return SEMA_OK;
+    }
+    const float *qd = q_dev;
+    if (s->ld != s->dim || (reinterpret_cast<uintptr_t>(q_dev) & 15)) {
+        CK(cudaMemcpyAsync(s->q_dev, q_dev, s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        qd = s->q_dev;
+    }
+    return scan_query(s, qd, (uint32_t)n, k, nullptr, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_topk_merge_device(sema_index *s, const uint64_t *keys_dev, uint32_t n_lists, uint32_t k,
+                           uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !keys_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u outside [1, %u]", k, SEMA_MAX_K);
+    if ((uint64_t)n_lists * k > 0x7fffffffull) return fail(SEMA_ERR_INVALID, "too many candidates");
+    CK(cudaSetDevice(s->device));
+    const uint32_t total = n_lists * k;
+    const bool l2 = s->metric == SEMA_METRIC_L2;
+    if (k <= (uint32_t)K_PASS)
+        return l2 ? merge_pass_m<METRIC_L2>(s, keys_dev, total, k, nullptr, nullptr, ids_dev, scores_dev, n_found_dev)
+                  : merge_pass_m<METRIC_COSINE>(s, keys_dev, total, k, nullptr, nullptr, ids_dev, scores_dev, n_found_dev);
+    uint64_t *keys = s->keys_dev;
+    for (uint32_t done = 0; done < k; done += K_PASS) {
+        const uint32_t kp = (k - done) < (uint32_t)K_PASS ? (k - done) : (uint32_t)K_PASS;
+        const uint64_t *bound = done ? keys + done - 1 : nullptr;
+        int rc = l2 ? merge_pass_m<METRIC_L2>(s, keys_dev, total, kp, bound, keys + done, nullptr, nullptr, nullptr)
+                    : merge_pass_m<METRIC_COSINE>(s, keys_dev, total, kp, bound, keys + done, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    return decode(s, keys, k, ids_dev, scores_dev, n_found_dev);
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// api_shard.cu — corpus-sharded group: scan + peer exchange + merge in one kernel per rank.
+#include "index_impl.cuh"
+#include "k2_scan.cuh"
+
+using namespace sema;
+using namespace sema_impl;
+
+extern "C" {
+
+// ---- corpus-sharded group with the fused peer exchange ---------------------------------
+struct sema_shard_group {
+    sema_index *idx = nullptr;
+    uint32_t world = 1, rank = 0;
+    uint64_t *xbuf = nullptr;                  // own exchange buffer (cudaMalloc: IPC-exportable)
+    uint64_t *peer[XCHG_MAX_WORLD] = {nullptr};
+    bool opened[XCHG_MAX_WORLD] = {false};
+    bool connected = false;
+    uint64_t seq = 0;
+};
+
+static size_t xbuf_bytes(uint32_t world) { return ((size_t)2 * world * XCHG_KEYS + (size_t)2 * world) * sizeof(uint64_t); }
+
+int sema_shard_group_create(sema_index *idx, uint32_t world, uint32_t rank, sema_shard_group **out)
+{
+    if (!idx || !out) return fail(SEMA_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (world < 1 || world > (uint32_t)XCHG_MAX_WORLD || rank >= world)
+        return fail(SEMA_ERR_INVALID, "world %u / rank %u outside [1, %d]", world, rank, XCHG_MAX_WORLD);
+    CK(cudaSetDevice(idx->device));
+    sema_shard_group *g = new (std::nothrow) sema_shard_group();
+    if (!g) return fail(SEMA_ERR_NOMEM, "host allocation failed");
+    g->idx = idx;
+    g->world = world;
+    g->rank = rank;
+    cudaError_t e = cudaMalloc(&g->xbuf, xbuf_bytes(world));
+    if (e == cudaSuccess) e = cudaMemset(g->xbuf, 0, xbuf_bytes(world));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(g->xbuf);
+        delete g;
+        return fail(SEMA_ERR_CUDA, "exchange buffer: %s", cudaGetErrorString(e));
+    }
+    g->peer[rank] = g->xbuf;
+    g->connected = world == 1;
+    *out = g;
+    return SEMA_OK;
+}
+
+int sema_shard_group_local_handle(sema_shard_group *g, void *handle_out)
+{
+    if (!g || !handle_out) return fail(SEMA_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SEMA_IPC_HANDLE_BYTES, "IPC handle size");
+    CK(cudaSetDevice(g->idx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, g->xbuf));
+    memcpy(handle_out, &h, sizeof h);
+    return SEMA_OK;
+}
+
+int sema_shard_group_connect(sema_shard_group *g, const void *handles)
+{
+    if (!g || !handles) return fail(SEMA_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(g->idx->device));
+    for (uint32_t r = 0; r < g->world; ++r) {
+        if (r == g->rank || g->opened[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const unsigned char *>(handles) + (size_t)r * SEMA_IPC_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        g->peer[r] = static_cast<uint64_t *>(p);
+        g->opened[r] = true;
+    }
+    g->connected = true;
+    return SEMA_OK;
+}
+
+static int group_scan(sema_shard_group *g, const float *q_dev, uint32_t k, uint64_t *ids_dev, float *scores_dev,
+                      uint32_t *nf_dev)
+{
+    sema_index *s = g->idx;
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    Exchange x;
+    memset(&x, 0, sizeof x);
+    for (uint32_t r = 0; r < g->world; ++r) x.peer[r] = g->peer[r];
+    x.world = g->world;
+    x.rank = g->rank;
+    x.seq = ++g->seq;
+    // an empty shard still takes part in the exchange: with n = 0 the kernel scans nothing
+    // (one block) and goes straight to publish / wait / merge
+    return scan_query(s, q_dev, (uint32_t)n, k, nullptr, ids_dev, scores_dev, nf_dev, &x);
+}
+
+int sema_shard_group_search_device(sema_shard_group *g, const float *q_dev, uint32_t k, uint64_t *ids_dev,
+                                   float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!g || !q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (!g->connected) return fail(SEMA_ERR_INVALID, "shard group not connected");
+    if (k == 0 || k > (uint32_t)K_PASS) return fail(SEMA_ERR_UNSUPPORTED, "fused shard search covers 1 <= k <= %d", K_PASS);
+    sema_index *s = g->idx;
+    CK(cudaSetDevice(s->device));
+    const float *qd = q_dev;
+    if (s->ld != s->dim || (reinterpret_cast<uintptr_t>(q_dev) & 15)) {
+        CK(cudaMemcpyAsync(s->q_dev, q_dev, s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        qd = s->q_dev;
+    }
+    return group_scan(g, qd, k, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uint64_t *row_ids, float *scores,
+                            uint32_t *n_found)
+{
+    if (!g || !q || !row_ids || !scores || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
+    if (!g->connected) return fail(SEMA_ERR_INVALID, "shard group not connected");
+    if (k == 0 || k > (uint32_t)K_PASS) return fail(SEMA_ERR_UNSUPPORTED, "fused shard search covers 1 <= k <= %d", K_PASS);
+    sema_index *s = g->idx;
+    CK(cudaSetDevice(s->device));
+    memcpy(s->q_pin, q, s->dim * sizeof(float));
+    CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (s->normalize_queries) {
+        int rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
+        if (rc) return rc;
+    }
+    uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
+    float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
+    int rc = group_scan(g, s->q_dev, k, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev));
+    if (rc) return rc;
+    const size_t bytes = 8 + 12 * (size_t)k;
+    CK(cudaMemcpyAsync(s->res_pin, s->res_dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const uint32_t nf = *reinterpret_cast<uint32_t *>(s->res_pin);
+    if (nf == 0xffffffffu) return fail(SEMA_ERR_CUDA, "shard exchange timed out: a rank did not take part in search %llu",
+                                       (unsigned long long)g->seq);
+    *n_found = nf;
+    memcpy(row_ids, s->res_pin + 8, nf * sizeof(uint64_t));
+    memcpy(scores, s->res_pin + 8 + 8 * (size_t)k, nf * sizeof(float));
+    return SEMA_OK;
+}
+
+int sema_shard_group_destroy(sema_shard_group *g)
+{
+    if (!g) return SEMA_OK;
+    cudaSetDevice(g->idx->device);
+    cudaStreamSynchronize(g->idx->stream);
+    for (uint32_t r = 0; r < g->world; ++r)
+        if (g->opened[r]) cudaIpcCloseMemHandle(g->peer[r]);
+    cudaFree(g->xbuf);
+    cudaGetLastError();
+    delete g;
+    return SEMA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// index_impl.cuh — internals shared by the translation units behind include/sema_b200.h.
+//
+// struct sema_index owns the HBM layout (row-major fp32, row stride ld = round_up(dim,4) floats,
+// base 256-byte aligned by cudaMalloc, so every row is 16-byte aligned), the streams and the small
+// staging buffers.  api_core.cu: lifecycle, ingest (K1), tombstones, compaction, disk cache,
+// properties.  api_search.cu: K2 / K4 dispatch and the single-query entry points.  api_batch.cu:
+// K3 (planes, cluster launch, re-scoring, fallback) and the batched entry points.  api_shard.cu:
+// the fused peer exchange.  No CPU fallback exists: every compute entry point needs a CUDA device.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <deque>
+#include <new>
+#include <vector>
+
+#include "../../include/sema_b200.h"
+#include "common.cuh"
+
+namespace sema_impl {
+
+int fail(int code, const char *fmt, ...);   // sets the thread-local error text, returns code
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return ::sema_impl::fail(SEMA_ERR_CUDA, "%s failed: %s (%s:%d)", #call,       \
+                                     cudaGetErrorString(e_), __FILE__, __LINE__);         \
+    } while (0)
+
+struct Pending {
+    cudaEvent_t ev;
+    uint64_t rows_after;
+};
+
+constexpr int K_PASS = 128;  // keys one fused pass can select (WarpTopK<4>)
+constexpr int MAX_BLOCKS_PER_SM = 8;
+
+}  // namespace sema_impl
+
+struct sema_index {
+    int device = 0;
+    uint32_t dim = 0, ld = 0;
+    uint64_t capacity = 0;
+    int metric = 0;
+    int num_sms = 0;
+    float *X = nullptr;
+    uint8_t *valid = nullptr;
+    uint64_t n_rows = 0;     // appended (enqueued)
+    uint64_t n_visible = 0;  // ingest completed on the device
+    uint64_t last_snapshot = 0;
+    uint32_t row_base = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, ingest_stream = nullptr;
+    float *q_dev = nullptr;           // ld floats
+    float *q_pin = nullptr;           // pinned, ld floats
+    uint64_t *partials = nullptr;     // num_sms * MAX_BLOCKS_PER_SM * 128 keys
+    unsigned int *ticket = nullptr;
+    uint64_t *keys_dev = nullptr;     // SEMA_MAX_K keys (multi-pass scratch)
+    unsigned char *res_dev = nullptr; // [n_found u32, pad][ids u64 K][scores f32 K]
+    unsigned char *res_pin = nullptr;
+    // batch buffers, grown on demand
+    float *Q_dev = nullptr;
+    uint64_t *bids_dev = nullptr;
+    float *bsc_dev = nullptr;
+    uint32_t *bnf_dev = nullptr;
+    size_t batch_cap_q = 0, batch_cap_res = 0;
+    uint64_t *tomb_dev = nullptr;
+    size_t tomb_cap = 0;
+    std::deque<sema_impl::Pending> pending;
+    int variant = 0;
+    uint64_t launches = 0;
+    // ---- K3 (batched tensor-core path) state
+    float *max_norm2 = nullptr;         // device: max squared row norm (written by K1)
+    unsigned char *planes = nullptr;    // pre-tiled bf16 hi/lo planes, built lazily
+    uint64_t planes_rows = 0;           // rows [0, planes_rows) are reflected in the planes
+    bool planes_failed = false;         // allocation failed once: stay on the K2 loop
+    float *Qpad_dev = nullptr;
+    uint32_t *cand_rows = nullptr;
+    float *cand_thr = nullptr;
+    uint32_t *flags_dev = nullptr, *flags_pin = nullptr;
+    size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
+    int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 bf16x3 whenever the shape allows, 3 K3 single bf16 pass
+    int k3_cluster = 0;                 // 0 auto, else forced cluster size (1, 2, 4) — tuning
+    int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
+    int normalize_queries = 0;          // apply K1 to host queries before scanning
+    unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch]
+    uint64_t k3_queries = 0, k3_fallbacks = 0;
+};
+
+namespace sema {
+struct Exchange;   // k2_scan.cuh
+}
+
+namespace sema_impl {
+
+// api_core.cu
+int poll_ingest(sema_index *s, bool wait);            // advance n_visible past completed ingests
+int ensure(void **p, size_t *cap, size_t need);       // grow a device scratch buffer
+int normalize_queries_dev(sema_index *s, float *q, uint64_t stride, uint32_t nq);   // K1 on queries, in place
+// api_search.cu: best k (any k <= SEMA_MAX_K) for one device-resident query; out_keys or res_* may be null
+int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys, uint64_t *res_ids,
+               float *res_scores, uint32_t *res_nfound, const sema::Exchange *x = nullptr);
+// api_batch.cu: nq device-resident queries (nq x dim dense); K3 when the shape allows, else K2 per query
+int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+               uint32_t *nf_d);
+
+}  // namespace sema_impl
