@@ -2,6 +2,7 @@
 #include "index_impl.cuh"
 #include "k2_scan.cuh"
 #include "k4_merge.cuh"
+#include "k2_scan_tma.cuh"
 
 using namespace sema;
 using namespace sema_impl;
@@ -60,6 +61,50 @@ int run_scan(sema_index *s, const ScanArgs &a)
     return SEMA_OK;
 }
 
+// rows reach the SM through a TMA bulk-copy ring (k2_scan_tma.cuh): the default for dim 384 / 768
+template <int NV, int M, int METRIC>
+int run_scan_tma(sema_index *s, const ScanArgs &a)
+{
+    auto kern = scan_topk_tma_kernel<NV, M, METRIC>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[s->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes<NV>()));
+        attr_set[s->device & 63] = true;
+    }
+    const uint32_t n_tiles = (a.n + tma_tile_rows<NV>() - 1) / tma_tile_rows<NV>();
+    uint32_t grid = (uint32_t)s->num_sms;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    ScanParams p;
+    p.X = reinterpret_cast<const float4 *>(s->X);
+    p.q = a.q_dev;
+    p.partials = s->partials;
+    p.ticket = s->ticket;
+    p.bound = a.bound;
+    p.out_keys = a.out_keys;
+    p.res_ids = a.res_ids;
+    p.res_scores = a.res_scores;
+    p.res_nfound = a.res_nfound;
+    p.n = a.n;
+    p.ld4 = s->ld / 4;
+    p.k = a.k;
+    p.row_base = s->row_base;
+    if (a.x) p.x = *a.x;
+    else memset(&p.x, 0, sizeof p.x);
+    kern<<<grid, TMA_THREADS, tma_smem_bytes<NV>(), s->stream>>>(p);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+template <int NV, int METRIC>
+int scan_tma_m(sema_index *s, const ScanArgs &a)
+{
+    if (a.k <= 32) return run_scan_tma<NV, 1, METRIC>(s, a);
+    if (a.k <= 64) return run_scan_tma<NV, 2, METRIC>(s, a);
+    return run_scan_tma<NV, 4, METRIC>(s, a);
+}
+
 template <int NV, int R, int METRIC>
 int scan_m(sema_index *s, const ScanArgs &a)
 {
@@ -72,17 +117,20 @@ template <int METRIC>
 int scan_shape(sema_index *s, const ScanArgs &a)
 {
     const uint32_t ld4 = s->ld / 4;
+    // variants: 0 = default (TMA ring), 1 / 2 / 3 = LDG kernel with R = 4 / 2 / 8 rows per warp batch
     if (ld4 == 96) {
         switch (s->variant) {
             case 1: return scan_m<3, 4, METRIC>(s, a);
             case 2: return scan_m<3, 2, METRIC>(s, a);
-            default: return scan_m<3, 8, METRIC>(s, a);   // R = 8: best or tied on every box measured
+            case 3: return scan_m<3, 8, METRIC>(s, a);
+            default: return scan_tma_m<3, METRIC>(s, a);
         }
     }
     if (ld4 == 192) {
         switch (s->variant) {
             case 1: return scan_m<6, 4, METRIC>(s, a);
-            default: return scan_m<6, 2, METRIC>(s, a);   // 24 float4 per lane per 4 rows is too many registers
+            case 2: return scan_m<6, 2, METRIC>(s, a);
+            default: return scan_tma_m<6, METRIC>(s, a);
         }
     }
     return scan_m<0, 4, METRIC>(s, a);

@@ -154,6 +154,107 @@ __device__ __forceinline__ void emit_results(const WarpTopK<M> &top, int k, uint
     if (res_nfound && lane == 0) *res_nfound = (uint32_t)found;
 }
 
+// Everything after a block's warps have scanned their rows, shared by the LDG and the TMA variant:
+// per-warp lists -> block list -> global partials; the last block to arrive (atomic ticket) merges
+// all block lists, optionally exchanges with the other shards (Exchange), and emits the result.
+// NW = warps in the block, NACTIVE = warps (0..NACTIVE-1) that hold lists / take part in the merges.
+template <int M>
+__device__ __forceinline__ void block_merge_n(WarpTopK<M> &top, uint64_t *sm, int warp, int lane, int k, int nw,
+                                              int nactive)
+{
+    (void)nw;
+    if (warp < nactive) top.store(sm + warp * 32 * M, lane);
+    __syncthreads();
+    if (warp == 0) {
+        const int chunks = (k + 31) >> 5;  // entries past k never matter
+        for (int w = 1; w < nactive; ++w)
+            for (int j = 0; j < chunks; ++j) {
+                const uint64_t key = sm[w * 32 * M + j * 32 + lane];
+                top.offer(key, key != 0, lane, k);
+            }
+    }
+}
+
+template <int M, int METRIC, int NW, int NACTIVE>
+__device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &p, uint64_t *sm_keys, bool *is_last,
+                                            int warp, int lane)
+{
+    const int k = (int)p.k;
+    block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
+    if (warp == 0) top.store(p.partials + (size_t)blockIdx.x * 32 * M, lane);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!*is_last) return;
+    __threadfence();
+
+    // Only the first k entries of each block list matter.  They are read as one flat array of
+    // gridDim.x * k keys, U independent loads per lane in flight: this merge sits on the critical
+    // path after the last block arrives, so its load latency must overlap, not add up.
+    top.init();
+    const int chunks = (k + 31) >> 5;
+    {
+        constexpr int U = 8;
+        const int totalk = (int)gridDim.x * k;
+        for (int base = warp * 32; warp < NACTIVE && base < totalk; base += NACTIVE * 32 * U) {
+            uint64_t kk[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = base + u * NACTIVE * 32 + lane;
+                const int bb = idx / k, e = idx - bb * k;
+                kk[u] = idx < totalk ? __ldcg(p.partials + (size_t)bb * 32 * M + e) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) top.offer(kk[u], kk[u] != 0, lane, k);
+        }
+    }
+    block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
+
+    bool timed_out = false;
+    if (p.x.world >= 1) {
+        // ---- fused exchange: publish the shard's top-k to every rank, wait for theirs, merge ----
+        const uint32_t world = p.x.world, slot = (uint32_t)(p.x.seq & 1);
+        uint64_t *mine = p.x.peer[p.x.rank];
+        if (warp == 0) {
+            for (uint32_t g = 0; g < world; ++g) {
+                uint64_t *dst = xchg_keys(p.x.peer[g], world, slot, p.x.rank);
+#pragma unroll
+                for (int j = 0; j < M; ++j) dst[j * 32 + lane] = (j * 32 + lane < k) ? top.v[j] : 0ull;
+            }
+            __threadfence_system();
+            __syncwarp();
+            if ((uint32_t)lane < world) st_release_sys(xchg_flag(p.x.peer[lane], world, slot, p.x.rank), p.x.seq);
+            bool ok = true;
+            if ((uint32_t)lane < world) {
+                const uint64_t *f = xchg_flag(mine, world, slot, (uint32_t)lane);
+                const long long t0 = clock64();
+                while (ld_acquire_sys(f) < p.x.seq) {
+                    if (clock64() - t0 > 4000000000ll) { ok = false; break; }   // ~2 s: a rank is missing
+                    __nanosleep(64);
+                }
+            }
+            ok = __all_sync(FULL, ok);
+            if (lane == 0) *is_last = ok;   // reuse the shared flag to broadcast the outcome
+        }
+        __syncthreads();
+        timed_out = !*is_last;
+        top.init();
+        const int total_x = (int)world * chunks;
+        for (int i = warp; warp < NACTIVE && i < total_x; i += NACTIVE) {
+            const int g = i / chunks, j = i - g * chunks;
+            const uint64_t key = __ldcv(xchg_keys(mine, world, slot, (uint32_t)g) + j * 32 + lane);
+            top.offer(key, key != 0, lane, k);
+        }
+        block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
+    }
+    if (warp == 0) {
+        emit_results<M, METRIC>(top, k, p.out_keys, p.res_ids, p.res_scores, p.res_nfound, lane);
+        if (timed_out && p.res_nfound && lane == 0) *p.res_nfound = 0xffffffffu;   // host reports the failure
+        if (lane == 0) *p.ticket = 0;
+    }
+}
+
 // NV > 0: row is exactly NV*32 float4 (unrolled, query in registers).
 // NV == 0: generic row length (query in shared memory, lane-strided loop).
 template <int NV, int R, int M, int METRIC>
@@ -231,80 +332,8 @@ scan_topk_kernel(const ScanParams p)
         top.offer(key, rep && row < n && s == s && key < bound, lane, k);
     }
 
-    // ---- block merge, then the last block to arrive merges all partial lists ----
-    block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
-    if (warp == 0) top.store(p.partials + (size_t)blockIdx.x * 32 * M, lane);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-
-    // Only the first k entries of each block list matter.  They are read as one flat array of
-    // gridDim.x * k keys, U independent loads per lane in flight: this merge sits on the critical
-    // path after the last block arrives, so its load latency must overlap, not add up.
-    top.init();
-    const int chunks = (k + 31) >> 5;
-    {
-        constexpr int U = 8;
-        const int totalk = (int)gridDim.x * k;
-        for (int base = warp * 32; base < totalk; base += SCAN_WARPS * 32 * U) {
-            uint64_t kk[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int idx = base + u * SCAN_WARPS * 32 + lane;
-                const int bb = idx / k, e = idx - bb * k;
-                kk[u] = idx < totalk ? __ldcg(p.partials + (size_t)bb * 32 * M + e) : 0ull;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) top.offer(kk[u], kk[u] != 0, lane, k);
-        }
-    }
-    block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
-
-    bool timed_out = false;
-    if (p.x.world >= 1) {
-        // ---- fused exchange: publish the shard's top-k to every rank, wait for theirs, merge ----
-        const uint32_t world = p.x.world, slot = (uint32_t)(p.x.seq & 1);
-        uint64_t *mine = p.x.peer[p.x.rank];
-        if (warp == 0) {
-            for (uint32_t g = 0; g < world; ++g) {
-                uint64_t *dst = xchg_keys(p.x.peer[g], world, slot, p.x.rank);
-#pragma unroll
-                for (int j = 0; j < M; ++j) dst[j * 32 + lane] = (j * 32 + lane < k) ? top.v[j] : 0ull;
-            }
-            __threadfence_system();
-            __syncwarp();
-            if ((uint32_t)lane < world) st_release_sys(xchg_flag(p.x.peer[lane], world, slot, p.x.rank), p.x.seq);
-            bool ok = true;
-            if ((uint32_t)lane < world) {
-                const uint64_t *f = xchg_flag(mine, world, slot, (uint32_t)lane);
-                const long long t0 = clock64();
-                while (ld_acquire_sys(f) < p.x.seq) {
-                    if (clock64() - t0 > 4000000000ll) { ok = false; break; }   // ~2 s: a rank is missing
-                    __nanosleep(64);
-                }
-            }
-            ok = __all_sync(FULL, ok);
-            if (lane == 0) is_last = ok;   // reuse the shared flag to broadcast the outcome
-        }
-        __syncthreads();
-        timed_out = !is_last;
-        top.init();
-        const int total_x = (int)world * chunks;
-        for (int i = warp; i < total_x; i += SCAN_WARPS) {
-            const int g = i / chunks, j = i - g * chunks;
-            const uint64_t key = __ldcv(xchg_keys(mine, world, slot, (uint32_t)g) + j * 32 + lane);
-            top.offer(key, key != 0, lane, k);
-        }
-        block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
-    }
-    if (warp == 0) {
-        emit_results<M, METRIC>(top, k, p.out_keys, p.res_ids, p.res_scores, p.res_nfound, lane);
-        if (timed_out && p.res_nfound && lane == 0) *p.res_nfound = 0xffffffffu;   // host reports the failure
-        if (lane == 0) *p.ticket = 0;
-    }
+    // ---- block merge, last-block merge, optional shard exchange, result emission ----
+    finish_topk<M, METRIC, SCAN_WARPS, SCAN_WARPS>(top, p, sm_keys, &is_last, warp, lane);
 }
 
 }  // namespace sema

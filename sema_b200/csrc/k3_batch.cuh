@@ -33,9 +33,12 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "k2_scan.cuh"
+#include "ptx.cuh"
 
 namespace sema {
 namespace k3 {
+
+using namespace ::sema::ptx;
 
 constexpr int TILE_Q = 128;            // queries per CTA (UMMA M)
 constexpr int TILE_N = 64;             // corpus rows per accumulator tile (UMMA N)
@@ -52,47 +55,7 @@ constexpr int MAX_DIM_1PASS = 768;     // single pass: q_hi alone needs dim/2 co
 // bytes of the pre-tiled planes per 64-row tile
 __host__ __device__ constexpr size_t tile_bytes(int dim) { return (size_t)TILE_N * dim * 4; }
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                 "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    // one asm block with scoped labels: no C-level loop, so the surrounding code stays
-    // warp-uniform for the compiler (uniform registers, no re-convergence scaffolding)
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "SEMA_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra SEMA_DONE;\n\t"
-        "bra SEMA_WAIT;\n\t"
-        "SEMA_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                 "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+// (generic mbarrier / bulk-copy wrappers live in ptx.cuh)
 // slice of a stage delivered to the same shared-memory offset of every CTA in cta_mask; each
 // destination CTA's mbarrier (same offset) receives the complete_tx for the bytes it got
 __device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
