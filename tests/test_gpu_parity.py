@@ -642,3 +642,17 @@ def test_randomized_shapes_against_oracle(sema, oracle_c):
                 r_ids, r_sc = oracle_c.scan(X, Q[i], k, metric, valid)
                 assert bnf[i] == len(r_ids)
                 O.check_parity(bids[i, :bnf[i]], bsc[i, :bnf[i]], r_ids, r_sc)
+
+
+def test_shard_group_with_an_empty_shard(sema):
+    # a rank whose row range is empty still takes part in the exchange (n = 0: nothing scanned)
+    with sema.GpuIndex(384, 8) as idx:
+        g = sema.ShardGroup(idx, 1, 0)
+        try:
+            ids, sc = g.search(np.ones(384, np.float32) / np.sqrt(384.0), 10)
+            assert len(ids) == 0 and len(sc) == 0
+            idx.append(_unit(1, 3, 384), normalize=False)
+            ids, sc = g.search(_unit(1, 3, 384)[1], 10)
+            assert ids.tolist()[0] == 1 and len(ids) == 3
+        finally:
+            g.close()
