@@ -33,11 +33,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n\t"
         ".reg .pred p;\n\t"
         "SEMA_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra SEMA_DONE;\n\t"
         "bra SEMA_WAIT;\n\t"
         "SEMA_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
