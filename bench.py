@@ -248,6 +248,25 @@ def run_batch(a):
             ids_h, sc_h, nf_h = idx.search_batch(Q, k)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
     served, fallbacks = idx.batch_stats()
+    # the same batch in automatic mode (precision cascade: single pass -> bf16x3 -> K2), for the record
+    auto = None
+    if a.batch_mode != 0:
+        idx.set_batch_mode(0)
+        idx.set_stream(stream.cuda_stream)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        auto_ms = e0.elapsed_time(e1) / steps
+        auto = {"ms_per_step": auto_ms, "value": nq / (auto_ms * 1e-3), "unit": "queries/s",
+                "algorithmic_tflops": 2.0 * nq * a.rows * a.dim / (auto_ms * 1e-3) / 1e12,
+                "cascaded_queries": idx.batch_cascaded}
+        idx.set_stream(None)
+        idx.set_batch_mode(a.batch_mode)
     # spot-check against the single-query kernel
     ok = True
     for i in (0, nq // 2, nq - 1):
@@ -275,6 +294,7 @@ def run_batch(a):
                 "d2h_bytes_per_step": nq * (k * 12 + 4), "ms_per_step": e2e_ms,
                 "path": "sema_index_search_batch (C ABI) with host buffers"},
         "gpu_launches": int(launches), "clocks": clk.summary(), "verified_against_k2": ok,
+        "auto_mode_cascade": auto,
     }
     print(json.dumps(line), flush=True)
 

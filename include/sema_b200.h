@@ -110,25 +110,28 @@ int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row
                       float *scores, uint32_t *n_found);
 /* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq].  With the
  * cosine metric, dim % 64 == 0, dim <= 768, k <= 100 and nq >= 4 this runs kernel K3 (tcgen05
- * tensor cores: bf16x3 split precision up to dim 384, a single bf16 pass for 384 < dim <= 768;
- * exact fp32 re-scoring of the candidates; needs a second dim*4 bytes per row of HBM for the bf16
- * planes, built on first use); otherwise, or if that memory cannot be had, K2 runs once per
- * query.  Results are identical either way. */
+ * tensor cores, bf16 split precision — see sema_index_set_batch_mode — with exact fp32
+ * re-scoring of the candidates; needs a second dim*4 bytes per row of HBM for the bf16 planes,
+ * built on first use); otherwise, or if that memory cannot be had, K2 runs once per query.
+ * Results are identical either way. */
 int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32_t k,
                             uint64_t *row_ids, float *scores, uint32_t *n_found);
 /* Same with queries and results resident on the device (Q_dev: nq x dim dense). */
 int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
-/* mode 0 = automatic (K3 with the bf16x3 split when the shape allows and nq >= 4), 1 = always K2
- * per query, 2 = K3 bf16x3 whenever the shape allows, 3 = K3 with a single bf16 pass as a coarser
- * candidate filter (a third of the tensor work; the exact fp32 re-scoring and the per-query
- * exactness proof are unchanged, so results are still identical — queries whose proof fails under
- * the looser 1-pass error bound are re-run through K2); other values only query.  Returns the
- * mode now active. */
+/* mode 0 = automatic: when the shape allows and nq >= 4, a precision cascade on the tensor cores —
+ * a single bf16 pass as a coarse candidate filter (a third of the tensor work), then the bf16x3
+ * split for the queries whose exactness proof failed under the looser single-pass error bound,
+ * then K2 for the few neither can prove (exact ties beyond the candidate list);
+ * 1 = always K2 per query; 2 = K3 bf16x3 only (+ K2 fallback); 3 = K3 single pass only (+ K2
+ * fallback).  Every path ends in the same exact fp32 re-scoring: results are identical.  Other
+ * values only query.  Returns the mode now active. */
 int sema_index_set_batch_mode(sema_index *idx, int mode);
-/* queries served by K3 so far, and how many of them were re-run through K2 because exactness
- * could not be proven from the candidate lists (heavy ties / duplicates). */
-int sema_index_batch_stats(const sema_index *idx, uint64_t *k3_queries, uint64_t *k3_fallbacks);
+/* queries served by K3 so far; how many of them were re-run through K2 because exactness could not
+ * be proven from the candidate lists (heavy ties / duplicates); how many went from the single-pass
+ * stage to the bf16x3 stage in automatic mode.  Any pointer may be NULL. */
+int sema_index_batch_stats(const sema_index *idx, uint64_t *k3_queries, uint64_t *k3_fallbacks,
+                           uint64_t *k3_cascaded);
 
 /* ---- device-resident variants (no host copies, no synchronisation) --------
  * Used for kernel-only timing and by the sharded path.  q_dev: dim floats on the

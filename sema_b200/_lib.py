@@ -49,7 +49,7 @@ SIGNATURES = {
     "sema_index_search_batch_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_index_set_normalize_queries": (C.c_int, [_vp, C.c_int]),
     "sema_index_set_batch_mode": (C.c_int, [_vp, C.c_int]),
-    "sema_index_batch_stats": (C.c_int, [_vp, _u64p, _u64p]),
+    "sema_index_batch_stats": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "sema_index_search_keys_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "sema_index_search_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
     "sema_topk_merge_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),

@@ -130,11 +130,13 @@ int k3_clusters(sema_index *s, int c, int *out)
 }
 
 // Qd: nq x dim dense on the device.  Results: device arrays [nq*k], [nq*k], [nq].
-int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
-             uint32_t *nf_d)
+// One K3 stage over nq device-resident queries: tensor-core scan with `passes` bf16 passes, exact fp32
+// re-scoring, exactness proof.  On return (stream synchronised) the results are in ids_d / sc_d / nf_d
+// and s->flags_pin[i] != 0 marks the queries whose proof failed; s->Qpad_dev holds the queries.
+int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, int passes, uint64_t *ids_d,
+             float *sc_d, uint32_t *nf_d)
 {
     const uint32_t kc = k <= 16 ? 32 : (k <= 48 ? 64 : 128);
-    const int passes = k3_passes(s, k);
     const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
     const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
     int rc;
@@ -218,14 +220,74 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         CK(cudaGetLastError());
         s->launches++;
     }
-    // queries whose exactness could not be proven (heavy ties / near-duplicates) go through K2
     CK(cudaMemcpyAsync(s->flags_pin, s->flags_dev, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return SEMA_OK;
+}
+
+// K3 for a batch.  Modes 2 / 3 run one stage (bf16x3 / single pass) and send the queries whose
+// exactness proof failed through K2.  Automatic mode is a precision cascade: the cheap single-pass
+// filter first (a third of the tensor work); the queries it cannot prove (corpora with dense
+// neighbourhoods: its error bound is 34x looser) are gathered and re-run with the bf16x3 split; what
+// even that cannot prove (exact ties beyond the candidate list) goes through K2.  Every path ends in
+// the same fp32 re-scoring, so the results are identical.
+int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+             uint32_t *nf_d)
+{
+    if (reinterpret_cast<uintptr_t>(Qd) & 15) {   // the kernels read queries as float4
+        int rc0 = ensure(reinterpret_cast<void **>(&s->q_aligned), &s->q_aligned_cap, (size_t)nq * s->dim * sizeof(float));
+        if (rc0) return rc0;
+        CK(cudaMemcpyAsync(s->q_aligned, Qd, (size_t)nq * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        Qd = s->q_aligned;
+    }
+    const bool can3 = s->dim <= (uint32_t)k3::MAX_DIM;
+    const bool cascade = s->batch_mode == 0 && can3;
+    const int passes = cascade ? 1 : k3_passes(s, k);
+    int rc = k3_stage(s, Qd, nq, n, k, passes, ids_d, sc_d, nf_d);
+    if (rc) return rc;
     s->k3_queries += nq;
-    for (uint32_t i = 0; i < nq; ++i) {
-        if (!s->flags_pin[i]) continue;
+    std::vector<uint32_t> open_q;   // queries still without a proven result
+    for (uint32_t i = 0; i < nq; ++i)
+        if (s->flags_pin[i]) open_q.push_back(i);
+    if (cascade && open_q.size() >= 4) {
+        s->k3_cascaded += open_q.size();
+        const uint32_t nsub = (uint32_t)open_q.size();
+        if ((size_t)nsub * 2 > nq) {
+            // most of the batch failed the loose bound: run the whole batch with the tight one
+            rc = k3_stage(s, Qd, nq, n, k, 3, ids_d, sc_d, nf_d);
+            if (rc) return rc;
+            open_q.clear();
+            for (uint32_t i = 0; i < nq; ++i)
+                if (s->flags_pin[i]) open_q.push_back(i);
+        } else {
+            rc = ensure(reinterpret_cast<void **>(&s->sub_q), &s->sub_q_cap, (size_t)nsub * s->dim * sizeof(float));
+            if (rc) return rc;
+            rc = ensure(reinterpret_cast<void **>(&s->sub_ids), &s->sub_ids_cap, (size_t)nsub * k * sizeof(uint64_t));
+            if (rc) return rc;
+            rc = ensure(reinterpret_cast<void **>(&s->sub_sc), &s->sub_sc_cap, (size_t)nsub * k * sizeof(float));
+            if (rc) return rc;
+            rc = ensure(reinterpret_cast<void **>(&s->sub_nf), &s->sub_nf_cap, (size_t)nsub * sizeof(uint32_t));
+            if (rc) return rc;
+            for (uint32_t j = 0; j < nsub; ++j)
+                CK(cudaMemcpyAsync(s->sub_q + (size_t)j * s->dim, Qd + (size_t)open_q[j] * s->dim, s->dim * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s->stream));
+            rc = k3_stage(s, s->sub_q, nsub, n, k, 3, s->sub_ids, s->sub_sc, s->sub_nf);
+            if (rc) return rc;
+            std::vector<uint32_t> still;
+            for (uint32_t j = 0; j < nsub; ++j) {
+                const uint32_t i = open_q[j];
+                if (s->flags_pin[j]) { still.push_back(i); continue; }
+                CK(cudaMemcpyAsync(ids_d + (size_t)i * k, s->sub_ids + (size_t)j * k, k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s->stream));
+                CK(cudaMemcpyAsync(sc_d + (size_t)i * k, s->sub_sc + (size_t)j * k, k * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+                CK(cudaMemcpyAsync(nf_d + i, s->sub_nf + j, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->stream));
+            }
+            open_q.swap(still);
+        }
+    }
+    // whatever no tensor-core stage could prove (heavy exact ties, near-duplicates) goes through K2
+    for (uint32_t i : open_q) {
         s->k3_fallbacks++;
-        rc = scan_query(s, s->Qpad_dev + (size_t)i * s->dim, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i);
+        rc = scan_query(s, Qd + (size_t)i * s->dim, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i);
         if (rc) return rc;
     }
     return SEMA_OK;
@@ -328,11 +390,12 @@ int sema_index_set_batch_mode(sema_index *s, int mode)
     return s->batch_mode;
 }
 
-int sema_index_batch_stats(const sema_index *s, uint64_t *k3_queries, uint64_t *k3_fallbacks)
+int sema_index_batch_stats(const sema_index *s, uint64_t *k3_queries, uint64_t *k3_fallbacks, uint64_t *k3_cascaded)
 {
     if (!s) return fail(SEMA_ERR_INVALID, "null index");
     if (k3_queries) *k3_queries = s->k3_queries;
     if (k3_fallbacks) *k3_fallbacks = s->k3_fallbacks;
+    if (k3_cascaded) *k3_cascaded = s->k3_cascaded;
     return SEMA_OK;
 }
 

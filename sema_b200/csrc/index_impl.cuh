@@ -88,7 +88,14 @@ struct sema_index {
     int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
     int normalize_queries = 0;          // apply K1 to host queries before scanning
     unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch]
-    uint64_t k3_queries = 0, k3_fallbacks = 0;
+    uint64_t k3_queries = 0, k3_fallbacks = 0, k3_cascaded = 0;
+    float *sub_q = nullptr;             // cascade: the queries the single-pass stage could not prove, and their results
+    uint64_t *sub_ids = nullptr;
+    float *sub_sc = nullptr;
+    uint32_t *sub_nf = nullptr;
+    size_t sub_q_cap = 0, sub_ids_cap = 0, sub_sc_cap = 0, sub_nf_cap = 0;
+    float *q_aligned = nullptr;         // 16-byte aligned copy of caller queries that are not
+    size_t q_aligned_cap = 0;
 };
 
 namespace sema {

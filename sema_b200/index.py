@@ -156,14 +156,21 @@ class GpuIndex:
         return self._L.sema_index_set_normalize_queries(self._h, int(on))
 
     def set_batch_mode(self, mode: int) -> int:
-        """0 = automatic, 1 = K2 once per query, 2 = K3 (tensor cores) whenever the shape allows."""
+        """0 = automatic (K3 precision cascade), 1 = K2 once per query, 2 = K3 bf16x3, 3 = K3 single pass."""
         return self._L.sema_index_set_batch_mode(self._h, mode)
 
     def batch_stats(self) -> tuple[int, int]:
         """-> (queries served by K3, of which re-run through K2 for lack of an exactness proof)."""
         a, b = C.c_uint64(), C.c_uint64()
-        check(self._L.sema_index_batch_stats(self._h, C.byref(a), C.byref(b)))
+        check(self._L.sema_index_batch_stats(self._h, C.byref(a), C.byref(b), None))
         return a.value, b.value
+
+    @property
+    def batch_cascaded(self) -> int:
+        """Queries that went from the single-pass K3 stage to the bf16x3 stage (automatic mode)."""
+        c = C.c_uint64()
+        check(self._L.sema_index_batch_stats(self._h, None, None, C.byref(c)))
+        return c.value
 
     def search_keys_device(self, q_ptr: int, k: int, keys_ptr: int) -> None:
         check(self._L.sema_index_search_keys_device(self._h, C.c_void_p(q_ptr), k, C.c_void_p(keys_ptr)))

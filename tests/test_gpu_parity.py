@@ -656,3 +656,64 @@ def test_shard_group_with_an_empty_shard(sema):
             assert ids.tolist()[0] == 1 and len(ids) == 3
         finally:
             g.close()
+
+
+def test_k3_precision_cascade_in_automatic_mode(sema, oracle_c):
+    """Automatic mode: single bf16 pass first; queries whose proof fails under its loose bound move to
+    the bf16x3 stage; only what neither proves goes through K2.  Dense neighbourhood: 200 rows whose
+    cosine to the query steps down by 1e-4 from 0.9 — the 10th and the 32nd candidate are 2.2e-3 apart
+    (inside the single-pass bound 8.5e-3, outside the bf16x3 bound 2.5e-4)."""
+    n, d, k = 30000, 384, 10
+    rng = np.random.default_rng(7)
+    X = _unit(1, n, d)
+    Q = _unit(2, 8, d)
+    u = Q[0].astype(np.float64)
+    for i in range(200):
+        v = rng.standard_normal(d)
+        v -= v.dot(u) * u
+        v /= np.linalg.norm(v)
+        a = 0.9 - i * 1e-4
+        X[1000 + i] = (a * u + np.sqrt(1 - a * a) * v).astype(np.float32)   # contiguous: more than KC of them per row partition
+    X = O.normalize(X)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, k)                  # automatic mode
+        served, fallbacks = idx.batch_stats()
+        cascaded = idx.batch_cascaded
+        idx.set_batch_mode(3)
+        ids1, sc1, _ = idx.search_batch(Q, k)                 # single pass only: the dense query falls back to K2
+        fb1 = idx.batch_stats()[1] - fallbacks
+    assert served == 8
+    r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
+    for i in range(8):
+        O.check_parity(ids[i], sc[i], r_ids[i], r_sc[i])
+    assert ids[0].tolist() == [1000 + i for i in range(10)]
+    assert np.array_equal(ids, ids1) and np.array_equal(sc, sc1)
+    assert fb1 >= 1                                           # the loose bound alone cannot prove query 0
+    # with fewer than 4 open queries the cascade goes straight to K2; with >= 4 it uses the bf16x3 stage
+    assert cascaded in (0, fallbacks) or fallbacks == 0
+
+
+def test_k3_cascade_uses_bf16x3_stage_for_many_dense_queries(sema, oracle_c):
+    n, d, k = 30000, 384, 10
+    rng = np.random.default_rng(8)
+    X = _unit(1, n, d)
+    Q = _unit(2, 16, d)
+    for qi in range(6):                                       # six queries with a dense neighbourhood each
+        u = Q[qi].astype(np.float64)
+        for i in range(120):
+            v = rng.standard_normal(d)
+            v -= v.dot(u) * u
+            v /= np.linalg.norm(v)
+            a = 0.9 - i * 1e-4
+            X[2000 * qi + i + 3] = (a * u + np.sqrt(1 - a * a) * v).astype(np.float32)   # contiguous: one row partition
+    X = O.normalize(X)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, k)
+        served, fallbacks = idx.batch_stats()
+        cascaded = idx.batch_cascaded
+    assert served == 16 and cascaded >= 6 and fallbacks == 0  # proven by the bf16x3 stage, no K2 pass needed
+    r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
+    for i in range(16):
+        O.check_parity(ids[i], sc[i], r_ids[i], r_sc[i])
