@@ -136,7 +136,9 @@ int k3_clusters(sema_index *s, int c, int *out)
 int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, int passes, uint64_t *ids_d,
              float *sc_d, uint32_t *nf_d)
 {
-    const uint32_t kc = k <= 16 ? 32 : (k <= 48 ? 64 : 128);
+    // candidates kept per (query, row partition): the list minimum is the admission threshold and every
+    // insertion re-scans the list, so the list is only as long as the exactness proof needs
+    const uint32_t kc = (k <= 10 && passes == 1 && s->k3_kc16 != 0) ? 16 : (k <= 16 ? 32 : (k <= 48 ? 64 : 128));
     const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
     const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
     int rc;
@@ -165,7 +167,7 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     CK(cudaMemcpyAsync(s->Qpad_dev, Qd, (size_t)nq * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
 
     int max_clusters = 1;
-    rc = kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
+    rc = kc == 16 ? k3_clusters<16>(s, csize, &max_clusters) : kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
     if (rc) return rc;
     const uint32_t groups_all = q_ctas_pad / csize;             // clusters along the query axis
     // at most max_clusters cluster columns per launch; the clusters left over become row partitions
@@ -191,7 +193,8 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         p.n_tiles = n_tiles;
         p.parts = parts;
         p.dim = s->dim;
-        rc = kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, csize, passes, qt_per_cta)
+        p.debug = (uint32_t)s->k3_debug;
+        rc = kc == 16 ? k3_launch_scan<16>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, csize, passes, qt_per_cta)
                       : k3_launch_scan<128>(s, p, q_ctas, csize, passes, qt_per_cta);
         if (rc) return rc;
         const uint32_t q_first = qt0 * k3::TILE_Q;

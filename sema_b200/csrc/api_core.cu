@@ -514,6 +514,8 @@ uint64_t sema_index_launch_count(const sema_index *s) { return s ? s->launches :
 int sema_index_set_scan_variant(sema_index *s, int variant)
 {
     if (!s) return -1;
+    if (variant >= 400) { s->k3_kc16 = variant - 400; return variant; }      // 400 = lists of 32, 401 = lists of 16 (k <= 10, single pass)
+    if (variant >= 300) { s->k3_debug = variant - 300; return variant; }     // timing experiments only
     if (variant >= 200) { s->k3_qt = variant - 200; return variant; }        // 200 = auto, 201 = one query tile per CTA
     if (variant >= 100) { s->k3_cluster = variant - 100; return variant; }   // 100 = auto, 101/102/104 = K3 cluster size
     if (variant >= 0) s->variant = variant;

@@ -85,6 +85,8 @@ struct sema_index {
     size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
     int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 bf16x3 whenever the shape allows, 3 K3 single bf16 pass
     int k3_cluster = 0;                 // 0 auto, else forced cluster size (1, 2, 4) — tuning
+    int k3_debug = 0;                   // timing experiments only (wrong results): see k3::Params::debug
+    int k3_kc16 = 1;                    // single-pass stage with k <= 10 keeps 16 candidates per list (0 = 32) — tuning
     int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
     int normalize_queries = 0;          // apply K1 to host queries before scanning
     unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch]

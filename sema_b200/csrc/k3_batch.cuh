@@ -210,6 +210,7 @@ struct Params {
     uint32_t n_tiles;             // ceil(n_rows / 64)
     uint32_t parts;               // row partitions (gridDim.y)
     uint32_t dim;
+    uint32_t debug;               // timing experiments only (wrong results): see the epilogue
 };
 
 // PASSES = 3: bf16x3 split (hi.hi + lo.hi + hi.lo), a stage holds the hi and lo plane blocks.
@@ -415,6 +416,7 @@ batch_scan_kernel(const Params p)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);   // MMA may overwrite this accumulator
                 const uint32_t row0 = t * TILE_N;
+                if (p.debug == 1) continue;                       // probe: no scan at all
                 // Pass 1 (unrolled, branch-free): which of my 64 scores beat the admission threshold?
                 uint32_t mask[2] = {0u, 0u};
 #pragma unroll
@@ -425,6 +427,7 @@ batch_scan_kernel(const Params p)
                 const uint32_t live = p.n_rows - row0;           // rows of this tile that exist (>= 1)
                 if (live < 32) { mask[0] &= (1u << live) - 1u; mask[1] = 0u; }
                 else if (live < 64) mask[1] &= (1u << (live - 32)) - 1u;
+                if (p.debug == 2) { if (mask[0] | mask[1]) thr = fmaxf(thr, -1e30f); continue; }   // probe: mask pass only
                 // Pass 2 (rare, not unrolled: keeps the instruction footprint small): insert them.
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -442,6 +445,7 @@ batch_scan_kernel(const Params p)
                         lsc[slot * TILE_Q + m] = v;
                         lrow[slot * TILE_Q + m] = row0 + h * 32 + c;
                         if (cnt < KC) ++cnt;
+                        if (p.debug == 3 && cnt == KC) { thr = fmaxf(thr, v * 0.5f); continue; }   // probe: no rescan
                         if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
                             float mn = lsc[m];
                             int mp = 0;
