@@ -190,7 +190,11 @@ int sema_index_set_normalize_queries(sema_index *idx, int on);
 uint64_t sema_index_last_snapshot(const sema_index *idx);
 /* copy stored (normalised) rows back to the host: out = n x dim floats */
 int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float *out);
-/* tuning: variant < 0 = default.  Returns the variant now active. */
+/* Tuning knob for measurements (results never change).  0 = default K2 kernel (TMA bulk-copy ring
+ * for dim 384 / 768), 1 / 2 / 3 = the register-fed K2 kernel with 4 / 2 / 8 rows per warp batch;
+ * 100 + c = K3 cluster size c (0 = automatic); 200 / 201 = K3 two / one query tiles per CTA in the
+ * single-pass stage; 300 + d = K3 timing probes (wrong results, timing only); 400 / 401 = K3
+ * single-pass candidate lists of 32 / 16 for k <= 10; negative = query.  Returns the value set. */
 int sema_index_set_scan_variant(sema_index *idx, int variant);
 /* number of kernels this handle has launched so far */
 uint64_t sema_index_launch_count(const sema_index *idx);

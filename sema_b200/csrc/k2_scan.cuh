@@ -1,4 +1,5 @@
-// k2_scan.cuh — kernel K2: single-query exact scan with fused top-k.
+// k2_scan.cuh — kernel K2: single-query exact scan with fused top-k (shared pieces + the
+// register-fed variant; the default TMA-ring variant is in k2_scan_tma.cuh).
 //
 // Replaces LanceDB's flat KNN behind table.query().nearest_to(q)?.limit(k).execute()
 // (reference: src/storage/lance_indexer.rs:121-126).  HBM-bandwidth bound: the
@@ -6,7 +7,7 @@
 // lives in registers, and selection never leaves the SM until the per-block lists
 // are merged by the last block to finish (single launch, graph-replayable).
 //
-// Work split: a warp owns batches of R consecutive rows.  A row is NV*32 float4
+// Work split (register-fed variant): a warp owns batches of R consecutive rows.  A row is NV*32 float4
 // (NV = 3 for d=384, 6 for d=768); lane l loads float4 l, l+32, ... of each row,
 // i.e. every warp-level LDG.128 covers 512 contiguous bytes.  The R partial sums
 // per lane are reduced with a transposed butterfly (R-1 + log2(32/R) shuffles per R
