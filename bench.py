@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="timed region: one search call per query instead of one query stream")
+    ap.add_argument("--no-chain", action="store_true", help="query stream without programmatic dependent launch (comparison)")
+    ap.add_argument("--staged-host-path", action="store_true", help="e2e through the staged H2D / D2H path (comparison)")
     return ap.parse_args()
 
 
@@ -499,6 +502,25 @@ def run_ours(a):
                 group = None
                 exchange = "nccl (fused unavailable on a peer)"
 
+    # the timed region issues its K queries as ONE query stream (one K2 launch per query, consecutive
+    # launches chained with programmatic dependent launch); --no-stream issues K separate calls
+    use_stream = (not a.no_stream) and (world == 1 or group is not None)
+    n_s = max(a.steps, a.warmup, 1)
+    Qs = Qd[torch.arange(n_s, device=dev) % a.queries].contiguous()      # query i of the stream = pool[i % pool]
+    ids_s = torch.zeros((n_s, k), dtype=torch.int64, device=dev)
+    sc_s = torch.zeros((n_s, k), dtype=torch.float32, device=dev)
+    nf_s = torch.zeros(n_s, dtype=torch.int32, device=dev)
+    if a.no_chain:
+        idx.set_scan_variant(600)
+
+    def run_device(nq):
+        if use_stream:
+            (idx if world == 1 else group).search_stream_device(Qs.data_ptr(), nq, k, ids_s.data_ptr(), sc_s.data_ptr(),
+                                                               nf_s.data_ptr())
+        else:
+            for i in range(nq):
+                step_device(i)
+
     def step_device(i):
         q = qptr[i % a.queries]
         if world == 1:
@@ -516,42 +538,47 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     # ---- device-timed region: inputs resident in HBM, CUDA events on the launching stream
-    for i in range(a.warmup):
-        step_device(i)
+    run_device(a.warmup)
     barrier()
     l0 = idx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
         e0.record(stream)
-        for i in range(a.steps):
-            step_device(i)
+        run_device(a.steps)
         e1.record(stream)
         barrier()
         dev_ms = e0.elapsed_time(e1)
         launches = idx.launch_count - l0
+        if use_stream:
+            ids_d.copy_(ids_s[a.steps - 1])
 
         # ---- end-to-end region: host query in, host results out, through the public call
         ids_h = np.zeros(k, dtype=np.uint64)
         sc_h = np.zeros(k, dtype=np.float32)
+        import ctypes
+        qh = [ctypes.c_void_p(Q[i].ctypes.data) for i in range(a.queries)]      # host pointers, built once
+        ids_p, sc_p = ctypes.c_void_p(ids_h.ctypes.data), ctypes.c_void_p(sc_h.ctypes.data)
         e2e_ms = None
+        if a.staged_host_path:
+            idx.set_scan_variant(500)
         if world == 1:
             idx.set_stream(None)
             for i in range(min(a.warmup, 5)):
-                idx.search_into(Q[i % a.queries], k, ids_h, sc_h)
+                idx.search_ptr(qh[i % a.queries], k, ids_p, sc_p)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for i in range(a.steps):
-                idx.search_into(Q[i % a.queries], k, ids_h, sc_h)
+                idx.search_ptr(qh[i % a.queries], k, ids_p, sc_p)
             torch.cuda.synchronize()
             e2e_ms = (time.perf_counter() - t0) * 1e3
         elif group is not None:
             for i in range(min(a.warmup, 5)):
-                group.search_into(Q[i % a.queries], k, ids_h, sc_h)
+                group.search_ptr(qh[i % a.queries], k, ids_p, sc_p)
             barrier()
             t0 = time.perf_counter()
             for i in range(a.steps):
-                group.search_into(Q[i % a.queries], k, ids_h, sc_h)
+                group.search_ptr(qh[i % a.queries], k, ids_p, sc_p)
             barrier()
             e2e_ms = (time.perf_counter() - t0) * 1e3
         else:
@@ -632,20 +659,24 @@ def run_ours(a):
                         f"{bytes_per_launch / L2_BYTES:.0f}x the 126 MB L2",
             "parallelism": "single GPU" if world == 1 else f"corpus row-sharded over {world} GPUs (one process each)",
             "exchange": exchange if world > 1 else None,
+            "issue": ("one query stream of K queries (sema_index_search_stream_device / sema_shard_group_search_stream_device): "
+                      "one K2 launch per query, " + ("unchained" if a.no_chain else "consecutive launches chained with programmatic dependent launch"))
+                     if use_stream else "one search call per query",
             "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks",
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": "profiles/r01_k2_scan_full_raw.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None,
             "algorithmic_bytes": bytes_per_launch, "peak_source": pk_src,
-            "kernel": "scan_topk_kernel (K2)",
+            "kernel": "scan_topk_tma_kernel (K2, TMA ring)" if (a.variant <= 0 and a.dim in (384, 768)) else "scan_topk_kernel (K2, register-fed)",
             "note": "achieved = rows_per_gpu*dim*4 bytes / device time per step (one K2 launch per step"
                     + ("" if world == 1 else ", which includes the top-k exchange and the global merge") + ")",
         },
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": ((a.dim + 3) // 4) * 16,
                 "d2h_bytes_per_step": 8 + 12 * k, "ms_per_step": e2e_ms / a.steps,
                 "path": ("sema_index_search" if world == 1 else "sema_shard_group_search" if group is not None else "sharded.ShardedSearcher.search")
-                        + " with host buffers: query H2D, K2 (+ exchange + merge), result D2H, stream sync"},
+                        + " with host buffers: the query travels in the kernel parameters (these bytes), K2 (+ exchange + merge) stores"
+                          " the result block into mapped host memory (these bytes), the call polls its completion flag"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "verified": verified,

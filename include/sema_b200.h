@@ -105,7 +105,10 @@ int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_i
  * Out (caller-allocated, k entries): row_ids = row_base + local row, best first;
  * scores = cosine (descending) or squared-L2 `_distance` (ascending).  Exact ties
  * rank the lower row id first.  *n_found = min(k, visible valid rows); an empty
- * index is SEMA_OK with *n_found = 0 (:108-111). */
+ * index is SEMA_OK with *n_found = 0 (:108-111).
+ * Cost of a call with dim 384 / 768 and k <= 128: ONE kernel launch and no copies — the query
+ * travels in the kernel's parameters and the last block stores the result block and a completion
+ * flag into mapped host memory, which this call polls. */
 int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row_ids,
                       float *scores, uint32_t *n_found);
 /* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq].  With the
@@ -119,6 +122,15 @@ int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32
 /* Same with queries and results resident on the device (Q_dev: nq x dim dense). */
 int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
+/* A query stream: nq independent single-query searches (kernel K2 once per query, one HBM pass
+ * each — the reference's own pattern of one nearest_to() call per query, lance_indexer.rs:121-126)
+ * issued back to back on the query stream.  With dim 384 / 768 and k <= 128 consecutive launches
+ * are chained with programmatic dependent launch: query i+1 starts scanning on the SMs query i has
+ * left while i's last block still merges, so the stream runs at the HBM rate without a per-query
+ * launch / merge gap.  Same layouts and results as sema_index_search_batch_device; all rows the
+ * stream sees are one snapshot. */
+int sema_index_search_stream_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
+                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
 /* mode 0 = automatic: when the shape allows and nq >= 4, a precision cascade on the tensor cores —
  * a single bf16 pass as a coarse candidate filter (a third of the tensor work), then the bf16x3
  * split for the queries whose exactness proof failed under the looser single-pass error bound,
@@ -170,6 +182,11 @@ int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uin
                             float *scores, uint32_t *n_found);
 int sema_shard_group_search_device(sema_shard_group *g, const float *q_dev, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
+/* nq group searches issued back to back (Q_dev: nq x dim, results nq x k); consecutive launches
+ * are chained like sema_index_search_stream_device, so a rank's next scan also overlaps the wait
+ * for its peers' keys. */
+int sema_shard_group_search_stream_device(sema_shard_group *g, const float *Q_dev, uint32_t nq, uint32_t k,
+                                          uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
 int sema_shard_group_destroy(sema_shard_group *g);
 
 /* ---- properties ------------------------------------------------------------ */
@@ -194,7 +211,9 @@ int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float 
  * for dim 384 / 768), 1 / 2 / 3 = the register-fed K2 kernel with 4 / 2 / 8 rows per warp batch;
  * 100 + c = K3 cluster size c (0 = automatic); 200 / 201 = K3 two / one query tiles per CTA in the
  * single-pass stage; 300 + d = K3 timing probes (wrong results, timing only); 400 / 401 = K3
- * single-pass candidate lists of 32 / 16 for k <= 10; negative = query.  Returns the value set. */
+ * single-pass candidate lists of 32 / 16 for k <= 10; 500 / 501 = host searches staged through
+ * H2D + D2H copies / query by kernel parameter + results to mapped host memory (default);
+ * 600 / 601 = query streams unchained / chained (default); negative = query.  Returns the value set. */
 int sema_index_set_scan_variant(sema_index *idx, int variant);
 /* number of kernels this handle has launched so far */
 uint64_t sema_index_launch_count(const sema_index *idx);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "sema_index_search": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _u32p]),
     "sema_index_search_batch": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_index_search_batch_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
+    "sema_index_search_stream_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_index_set_normalize_queries": (C.c_int, [_vp, C.c_int]),
     "sema_index_set_batch_mode": (C.c_int, [_vp, C.c_int]),
     "sema_index_batch_stats": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "sema_shard_group_connect": (C.c_int, [_vp, _vp]),
     "sema_shard_group_search": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _u32p]),
     "sema_shard_group_search_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
+    "sema_shard_group_search_stream_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_shard_group_destroy": (C.c_int, [_vp]),
     "sema_index_set_row_base": (C.c_int, [_vp, C.c_uint64]),
     "sema_index_set_stream": (C.c_int, [_vp, _vp, C.c_int]),

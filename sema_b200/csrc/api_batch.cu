@@ -310,9 +310,18 @@ int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t
         if (rc == SEMA_OK) return k3_batch(s, Qd, nq, n, k, ids_d, sc_d, nf_d);
         if (rc != SEMA_ERR_NOMEM) return rc;
     }
-    // K2 once per query (still one HBM pass per query)
+    return scan_stream(s, Qd, nq, n, k, ids_d, sc_d, nf_d, nullptr, nullptr);
+}
+
+// K2 once per query (one HBM pass each), issued back to back.  With the TMA kernel and k <= 128
+// launch i+1 is chained to launch i (programmatic dependent launch): its scan starts on the SMs
+// launch i has left while i's last block still merges (and, sharded, exchanges with the peers).
+// x / seq: optional shard exchange; *seq is advanced once per query.
+int scan_stream(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+                uint32_t *nf_d, sema::Exchange *x, uint64_t *seq)
+{
     const float *Qp = Qd;
-    if (s->ld != s->dim) {
+    if (s->ld != s->dim || (reinterpret_cast<uintptr_t>(Qd) & 15)) {
         int rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, (size_t)nq * s->ld * sizeof(float));
         if (rc) return rc;
         CK(cudaMemsetAsync(s->Qpad_dev, 0, (size_t)nq * s->ld * sizeof(float), s->stream));
@@ -321,7 +330,10 @@ int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t
         Qp = s->Qpad_dev;
     }
     for (uint32_t i = 0; i < nq; ++i) {
-        int rc = scan_query(s, Qp + (size_t)i * s->ld, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i);
+        if (x) x->seq = ++*seq;
+        const unsigned flags = (i > 0 && s->chain) ? SCAN_CHAINED : 0u;
+        int rc = scan_query(s, Qp + (size_t)i * s->ld, n, k, nullptr, ids_d + (size_t)i * k, sc_d + (size_t)i * k, nf_d + i,
+                            x, flags);
         if (rc) return rc;
     }
     return SEMA_OK;
@@ -384,6 +396,23 @@ int sema_index_search_batch_device(sema_index *s, const float *Q_dev, uint32_t n
         return SEMA_OK;
     }
     return batch_core(s, Q_dev, nq, (uint32_t)n, k, ids_dev, scores_dev, n_found_dev);
+}
+
+int sema_index_search_stream_device(sema_index *s, const float *Q_dev, uint32_t nq, uint32_t k,
+                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !Q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K || nq == 0) return fail(SEMA_ERR_INVALID, "k %u / nq %u out of range", k, nq);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(n_found_dev, 0, (size_t)nq * sizeof(uint32_t), s->stream));
+        return SEMA_OK;
+    }
+    return scan_stream(s, Q_dev, nq, (uint32_t)n, k, ids_dev, scores_dev, n_found_dev, nullptr, nullptr);
 }
 
 int sema_index_set_batch_mode(sema_index *s, int mode)

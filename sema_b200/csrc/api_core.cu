@@ -183,14 +183,19 @@ int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metr
     CKD(cudaHostAlloc(&s->q_pin, s->ld * sizeof(float), cudaHostAllocPortable));
     memset(s->q_pin, 0, s->ld * sizeof(float));
     CKD(cudaMalloc(&s->partials, (size_t)s->num_sms * MAX_BLOCKS_PER_SM * K_PASS * sizeof(uint64_t)));
-    CKD(cudaMalloc(&s->ticket, 2 * sizeof(unsigned int)));
-    CKD(cudaMemset(s->ticket, 0, 2 * sizeof(unsigned int)));
+    CKD(cudaMalloc(&s->ticket, 4 * sizeof(unsigned int)));
+    CKD(cudaMemset(s->ticket, 0, 4 * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
     CKD(cudaMalloc(&s->max_norm2, sizeof(float)));
     CKD(cudaMalloc(&s->qscratch, 65536 + 16));
     CKD(cudaMemset(s->max_norm2, 0, sizeof(float)));
     CKD(cudaMalloc(&s->res_dev, res_bytes));
     CKD(cudaHostAlloc(&s->res_pin, res_bytes, cudaHostAllocPortable));
+    // mapped result block of the host-query path: the kernel stores results + completion flag here
+    CKD(cudaHostAlloc(&s->res_map, RES_MAP_BYTES, cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(s->res_map, 0, RES_MAP_BYTES);
+    CKD(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->res_map_dev), s->res_map, 0));
+    s->host_flag = reinterpret_cast<uint64_t *>(s->res_map_dev + RES_MAP_FLAG_OFF);
     CKD(cudaDeviceSynchronize());
 #undef CKD
     *out = s;
@@ -206,7 +211,7 @@ int sema_index_destroy(sema_index *s)
     for (auto &p : s->pending) cudaEventDestroy(p.ev);
     cudaFree(s->X); cudaFree(s->valid); cudaFree(s->q_dev); cudaFreeHost(s->q_pin);
     cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->keys_dev); cudaFree(s->res_dev);
-    cudaFreeHost(s->res_pin); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
+    cudaFreeHost(s->res_pin); cudaFreeHost(s->res_map); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
     cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
     cudaFree(s->qscratch); cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
     cudaFree(s->q_aligned); cudaFree(s->sub_q); cudaFree(s->sub_ids); cudaFree(s->sub_sc); cudaFree(s->sub_nf);
@@ -514,6 +519,8 @@ uint64_t sema_index_launch_count(const sema_index *s) { return s ? s->launches :
 int sema_index_set_scan_variant(sema_index *s, int variant)
 {
     if (!s) return -1;
+    if (variant >= 600) { s->chain = variant - 600; return variant; }        // 600 / 601 = query streams unchained / chained (PDL)
+    if (variant >= 500) { s->host_path = variant - 500; return variant; }    // 500 / 501 = host searches staged through H2D + D2H / query by kernel parameter + mapped results
     if (variant >= 400) { s->k3_kc16 = variant - 400; return variant; }      // 400 = lists of 32, 401 = lists of 16 (k <= 10, single pass)
     if (variant >= 300) { s->k3_debug = variant - 300; return variant; }     // timing experiments only
     if (variant >= 200) { s->k3_qt = variant - 200; return variant; }        // 200 = auto, 201 = one query tile per CTA

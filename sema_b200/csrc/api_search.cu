@@ -19,7 +19,30 @@ struct ScanArgs {
     float *res_scores;
     uint32_t *res_nfound;
     const Exchange *x = nullptr;   // sharded mode: fused peer exchange (single pass only)
+    unsigned flags = 0;            // SCAN_CHAINED, SCAN_HOST_QUERY (index_impl.cuh)
 };
+
+void fill_params(sema_index *s, const ScanArgs &a, ScanParams &p)
+{
+    p.X = reinterpret_cast<const float4 *>(s->X);
+    p.q = a.q_dev;
+    p.partials = s->partials;
+    p.ticket = s->ticket;
+    p.bound = a.bound;
+    p.out_keys = a.out_keys;
+    p.res_ids = a.res_ids;
+    p.res_scores = a.res_scores;
+    p.res_nfound = a.res_nfound;
+    p.n = a.n;
+    p.ld4 = s->ld / 4;
+    p.k = a.k;
+    p.row_base = s->row_base;
+    p.work_ctr = nullptr;
+    p.host_flag = nullptr;
+    p.host_seq = 0;
+    if (a.x) p.x = *a.x;
+    else memset(&p.x, 0, sizeof p.x);
+}
 
 template <int NV, int R, int M, int METRIC>
 int run_scan(sema_index *s, const ScanArgs &a)
@@ -40,32 +63,20 @@ int run_scan(sema_index *s, const ScanArgs &a)
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     ScanParams p;
-    p.X = reinterpret_cast<const float4 *>(s->X);
-    p.q = a.q_dev;
-    p.partials = s->partials;
-    p.ticket = s->ticket;
-    p.bound = a.bound;
-    p.out_keys = a.out_keys;
-    p.res_ids = a.res_ids;
-    p.res_scores = a.res_scores;
-    p.res_nfound = a.res_nfound;
-    p.n = a.n;
-    p.ld4 = s->ld / 4;
-    p.k = a.k;
-    p.row_base = s->row_base;
-    if (a.x) p.x = *a.x;
-    else memset(&p.x, 0, sizeof p.x);
+    fill_params(s, a, p);
     kern<<<grid, SCAN_THREADS, dyn, s->stream>>>(p);
     CK(cudaGetLastError());
     s->launches++;
     return SEMA_OK;
 }
 
-// rows reach the SM through a TMA bulk-copy ring (k2_scan_tma.cuh): the default for dim 384 / 768
-template <int NV, int M, int METRIC>
+// rows reach the SM through a TMA bulk-copy ring (k2_scan_tma.cuh): the default for dim 384 / 768.
+// QP: the query travels as a kernel parameter (a.q_dev is then a HOST pointer to dim floats) and the
+// results / completion flag go to the handle's mapped host buffer.
+template <int NV, int M, int METRIC, bool QP>
 int run_scan_tma(sema_index *s, const ScanArgs &a)
 {
-    auto kern = scan_topk_tma_kernel<NV, M, METRIC>;
+    auto kern = scan_topk_tma_kernel<NV, M, METRIC, QP>;
     static bool attr_set[64] = {false};
     if (!attr_set[s->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes<NV>()));
@@ -76,23 +87,31 @@ int run_scan_tma(sema_index *s, const ScanArgs &a)
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     ScanParams p;
-    p.X = reinterpret_cast<const float4 *>(s->X);
-    p.q = a.q_dev;
-    p.partials = s->partials;
-    p.ticket = s->ticket;
-    p.bound = a.bound;
-    p.out_keys = a.out_keys;
-    p.res_ids = a.res_ids;
-    p.res_scores = a.res_scores;
-    p.res_nfound = a.res_nfound;
-    p.n = a.n;
-    p.ld4 = s->ld / 4;
-    p.k = a.k;
-    p.row_base = s->row_base;
-    if (a.x) p.x = *a.x;
-    else memset(&p.x, 0, sizeof p.x);
-    kern<<<grid, TMA_THREADS, tma_smem_bytes<NV>(), s->stream>>>(p);
-    CK(cudaGetLastError());
+    fill_params(s, a, p);
+    p.work_ctr = s->ticket + 2 + (s->scan_seq++ & 1);   // alternate: a chained launch overlaps its predecessor
+    QueryArg<QP ? NV : 0> qa;
+    if constexpr (QP) {
+        static_assert(sizeof(ScanParams) + sizeof(qa) <= 4096, "kernel parameter space");
+        memcpy(qa.v, a.q_dev, s->dim * sizeof(float));   // ld == dim for these shapes
+        p.q = nullptr;
+        p.host_flag = s->host_flag;
+        p.host_seq = ++s->host_seq;
+    } else {
+        qa.unused = 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TMA_THREADS);
+    cfg.dynamicSmemBytes = tma_smem_bytes<NV>();
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    // only a launch that directly follows another TMA scan of the same call may overlap it; `bound`
+    // (multi-pass) is read at kernel start and is produced by the predecessor, so it never chains
+    cfg.numAttrs = ((a.flags & SCAN_CHAINED) && !a.bound) ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, p, qa));
     s->launches++;
     return SEMA_OK;
 }
@@ -100,9 +119,14 @@ int run_scan_tma(sema_index *s, const ScanArgs &a)
 template <int NV, int METRIC>
 int scan_tma_m(sema_index *s, const ScanArgs &a)
 {
-    if (a.k <= 32) return run_scan_tma<NV, 1, METRIC>(s, a);
-    if (a.k <= 64) return run_scan_tma<NV, 2, METRIC>(s, a);
-    return run_scan_tma<NV, 4, METRIC>(s, a);
+    if (a.flags & SCAN_HOST_QUERY) {
+        if (a.k <= 32) return run_scan_tma<NV, 1, METRIC, true>(s, a);
+        if (a.k <= 64) return run_scan_tma<NV, 2, METRIC, true>(s, a);
+        return run_scan_tma<NV, 4, METRIC, true>(s, a);
+    }
+    if (a.k <= 32) return run_scan_tma<NV, 1, METRIC, false>(s, a);
+    if (a.k <= 64) return run_scan_tma<NV, 2, METRIC, false>(s, a);
+    return run_scan_tma<NV, 4, METRIC, false>(s, a);
 }
 
 template <int NV, int R, int METRIC>
@@ -175,12 +199,13 @@ int decode(sema_index *s, const uint64_t *keys, uint32_t k, uint64_t *ids, float
 namespace sema_impl {
 
 int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys,
-               uint64_t *res_ids, float *res_scores, uint32_t *res_nfound, const Exchange *x)
+               uint64_t *res_ids, float *res_scores, uint32_t *res_nfound, const Exchange *x, unsigned flags)
 {
     if (k <= K_PASS) {
-        ScanArgs a{q_dev, n, k, nullptr, out_keys ? out_keys : s->keys_dev, res_ids, res_scores, res_nfound, x};
+        ScanArgs a{q_dev, n, k, nullptr, out_keys ? out_keys : s->keys_dev, res_ids, res_scores, res_nfound, x, flags};
         return scan_pass(s, a);
     }
+    if (flags & SCAN_HOST_QUERY) return fail(SEMA_ERR_UNSUPPORTED, "the host-query path covers k <= %d", K_PASS);
     if (x) return fail(SEMA_ERR_UNSUPPORTED, "the fused shard exchange covers k <= %d", K_PASS);
     uint64_t *keys = out_keys ? out_keys : s->keys_dev;
     for (uint32_t done = 0; done < k; done += K_PASS) {
@@ -190,6 +215,49 @@ int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64
         if (rc) return rc;
     }
     if (res_ids) return decode(s, keys, k, res_ids, res_scores, res_nfound);
+    return SEMA_OK;
+}
+
+bool host_query_ok(const sema_index *s, uint32_t k)
+{
+    const uint32_t ld4 = s->ld / 4;
+    return s->host_path && s->variant == 0 && !s->normalize_queries && k >= 1 && k <= (uint32_t)K_PASS &&
+           s->ld == s->dim && (ld4 == 96 || ld4 == 192) && s->res_map != nullptr;
+}
+
+int host_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const Exchange *x, uint64_t *row_ids,
+                   float *scores, uint32_t *n_found)
+{
+    uint64_t *ids_m = reinterpret_cast<uint64_t *>(s->res_map_dev + 8);
+    float *sc_m = reinterpret_cast<float *>(s->res_map_dev + 8 + 8 * (size_t)k);
+    int rc = scan_query(s, q_host, n, k, nullptr, ids_m, sc_m, reinterpret_cast<uint32_t *>(s->res_map_dev), x,
+                        SCAN_HOST_QUERY);
+    if (rc) return rc;
+    // Poll the flag the last block stores after the results.  The stream is queried now and then so
+    // that a failed launch / faulting kernel surfaces as an error instead of an endless wait.
+    const uint64_t want = s->host_seq;
+    volatile const uint64_t *flag = reinterpret_cast<volatile const uint64_t *>(s->res_map + RES_MAP_FLAG_OFF);
+    for (uint32_t spin = 1;; ++spin) {
+        if (*flag == want) break;
+        if ((spin & 0x3fffu) == 0) {
+            const cudaError_t e = cudaStreamQuery(s->stream);
+            if (e == cudaSuccess) {
+                if (*flag == want) break;
+                return fail(SEMA_ERR_CUDA, "scan finished without publishing its result");
+            }
+            if (e != cudaErrorNotReady)
+                return fail(SEMA_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    const uint32_t nf = *reinterpret_cast<const uint32_t *>(s->res_map);
+    if (nf == 0xffffffffu) return fail(SEMA_ERR_CUDA, "shard exchange timed out: a rank did not take part in the search");
+    *n_found = nf;
+    memcpy(row_ids, s->res_map + 8, nf * sizeof(uint64_t));
+    memcpy(scores, s->res_map + 8 + 8 * (size_t)k, nf * sizeof(float));
     return SEMA_OK;
 }
 
@@ -210,6 +278,7 @@ int sema_index_search(sema_index *s, const float *q, uint32_t k, uint64_t *row_i
     s->last_snapshot = n;
     *n_found = 0;
     if (k == 0 || n == 0) return SEMA_OK;
+    if (host_query_ok(s, k)) return host_query_run(s, q, (uint32_t)n, k, nullptr, row_ids, scores, n_found);
     memcpy(s->q_pin, q, s->dim * sizeof(float));
     CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     if (s->normalize_queries) {

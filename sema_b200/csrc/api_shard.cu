@@ -74,58 +74,72 @@ int sema_shard_group_connect(sema_shard_group *g, const void *handles)
     return SEMA_OK;
 }
 
-static int group_scan(sema_shard_group *g, const float *q_dev, uint32_t k, uint64_t *ids_dev, float *scores_dev,
-                      uint32_t *nf_dev)
+static void group_exchange(const sema_shard_group *g, Exchange &x)
 {
-    sema_index *s = g->idx;
-    int rc = poll_ingest(s, false);
-    if (rc) return rc;
-    const uint64_t n = s->n_visible;
-    s->last_snapshot = n;
-    Exchange x;
     memset(&x, 0, sizeof x);
     for (uint32_t r = 0; r < g->world; ++r) x.peer[r] = g->peer[r];
     x.world = g->world;
     x.rank = g->rank;
-    x.seq = ++g->seq;
-    // an empty shard still takes part in the exchange: with n = 0 the kernel scans nothing
-    // (one block) and goes straight to publish / wait / merge
-    return scan_query(s, q_dev, (uint32_t)n, k, nullptr, ids_dev, scores_dev, nf_dev, &x);
+}
+
+// An empty shard still takes part in the exchange: with n = 0 the kernel scans nothing (one block)
+// and goes straight to publish / wait / merge.
+static int group_check(sema_shard_group *g, uint32_t k)
+{
+    if (!g->connected) return fail(SEMA_ERR_INVALID, "shard group not connected");
+    if (k == 0 || k > (uint32_t)K_PASS) return fail(SEMA_ERR_UNSUPPORTED, "fused shard search covers 1 <= k <= %d", K_PASS);
+    return SEMA_OK;
+}
+
+int sema_shard_group_search_stream_device(sema_shard_group *g, const float *Q_dev, uint32_t nq, uint32_t k,
+                                          uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!g || !Q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (nq == 0) return fail(SEMA_ERR_INVALID, "nq = 0");
+    int rc = group_check(g, k);
+    if (rc) return rc;
+    sema_index *s = g->idx;
+    CK(cudaSetDevice(s->device));
+    rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    Exchange x;
+    group_exchange(g, x);
+    return scan_stream(s, Q_dev, nq, (uint32_t)n, k, ids_dev, scores_dev, n_found_dev, &x, &g->seq);
 }
 
 int sema_shard_group_search_device(sema_shard_group *g, const float *q_dev, uint32_t k, uint64_t *ids_dev,
                                    float *scores_dev, uint32_t *n_found_dev)
 {
-    if (!g || !q_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
-    if (!g->connected) return fail(SEMA_ERR_INVALID, "shard group not connected");
-    if (k == 0 || k > (uint32_t)K_PASS) return fail(SEMA_ERR_UNSUPPORTED, "fused shard search covers 1 <= k <= %d", K_PASS);
-    sema_index *s = g->idx;
-    CK(cudaSetDevice(s->device));
-    const float *qd = q_dev;
-    if (s->ld != s->dim || (reinterpret_cast<uintptr_t>(q_dev) & 15)) {
-        CK(cudaMemcpyAsync(s->q_dev, q_dev, s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        qd = s->q_dev;
-    }
-    return group_scan(g, qd, k, ids_dev, scores_dev, n_found_dev);
+    return sema_shard_group_search_stream_device(g, q_dev, 1, k, ids_dev, scores_dev, n_found_dev);
 }
 
 int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uint64_t *row_ids, float *scores,
                             uint32_t *n_found)
 {
     if (!g || !q || !row_ids || !scores || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
-    if (!g->connected) return fail(SEMA_ERR_INVALID, "shard group not connected");
-    if (k == 0 || k > (uint32_t)K_PASS) return fail(SEMA_ERR_UNSUPPORTED, "fused shard search covers 1 <= k <= %d", K_PASS);
+    int rc = group_check(g, k);
+    if (rc) return rc;
     sema_index *s = g->idx;
     CK(cudaSetDevice(s->device));
+    rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    Exchange x;
+    group_exchange(g, x);
+    x.seq = ++g->seq;
+    if (host_query_ok(s, k)) return host_query_run(s, q, (uint32_t)n, k, &x, row_ids, scores, n_found);
     memcpy(s->q_pin, q, s->dim * sizeof(float));
     CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     if (s->normalize_queries) {
-        int rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
+        rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
         if (rc) return rc;
     }
     uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
     float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
-    int rc = group_scan(g, s->q_dev, k, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev));
+    rc = scan_query(s, s->q_dev, (uint32_t)n, k, nullptr, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev), &x);
     if (rc) return rc;
     const size_t bytes = 8 + 12 * (size_t)k;
     CK(cudaMemcpyAsync(s->res_pin, s->res_dev, bytes, cudaMemcpyDeviceToHost, s->stream));

@@ -40,6 +40,13 @@ struct Pending {
 constexpr int K_PASS = 128;  // keys one fused pass can select (WarpTopK<4>)
 constexpr int MAX_BLOCKS_PER_SM = 8;
 
+// scan_query flags
+constexpr unsigned SCAN_CHAINED = 1u;      // directly follows another scan of the same call: may overlap it (PDL)
+constexpr unsigned SCAN_HOST_QUERY = 2u;   // q is a HOST pointer; query by kernel parameter, results + flag to res_map
+
+constexpr size_t RES_MAP_BYTES = 4096;     // mapped result block: [n_found u32, pad][ids u64 k][scores f32 k] ... [flag u64 @ 2048]
+constexpr size_t RES_MAP_FLAG_OFF = 2048;
+
 }  // namespace sema_impl
 
 struct sema_index {
@@ -58,7 +65,14 @@ struct sema_index {
     float *q_dev = nullptr;           // ld floats
     float *q_pin = nullptr;           // pinned, ld floats
     uint64_t *partials = nullptr;     // num_sms * MAX_BLOCKS_PER_SM * 128 keys
-    unsigned int *ticket = nullptr;
+    unsigned int *ticket = nullptr;   // [0] arrival ticket, [2], [3] tile-claim counters of the TMA scan (alternating)
+    uint64_t scan_seq = 0;            // TMA scans launched (selects the claim counter)
+    unsigned char *res_map = nullptr; // mapped pinned host memory the host-query path writes results to (RES_MAP_BYTES)
+    unsigned char *res_map_dev = nullptr;   // its device address
+    uint64_t *host_flag = nullptr;    // device address of the completion flag inside res_map
+    uint64_t host_seq = 0;            // value the next host-query launch will store there
+    int chain = 1;                    // 0 = query streams never chain consecutive scans with PDL (tuning / comparison)
+    int host_path = 1;                // 0 = host searches always stage through q_dev / res_dev (tuning / comparison)
     uint64_t *keys_dev = nullptr;     // SEMA_MAX_K keys (multi-pass scratch)
     unsigned char *res_dev = nullptr; // [n_found u32, pad][ids u64 K][scores f32 K]
     unsigned char *res_pin = nullptr;
@@ -112,9 +126,20 @@ int ensure(void **p, size_t *cap, size_t need);       // grow a device scratch b
 int normalize_queries_dev(sema_index *s, float *q, uint64_t stride, uint32_t nq);   // K1 on queries, in place
 // api_search.cu: best k (any k <= SEMA_MAX_K) for one device-resident query; out_keys or res_* may be null
 int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys, uint64_t *res_ids,
-               float *res_scores, uint32_t *res_nfound, const sema::Exchange *x = nullptr);
+               float *res_scores, uint32_t *res_nfound, const sema::Exchange *x = nullptr, unsigned flags = 0);
+// Host-query fast path (single fused pass on the TMA kernel): the query rides in the kernel
+// parameters and the last block writes the result block + a completion flag straight into mapped
+// host memory, so a search costs one launch and no copies.  host_query_ok: does this handle /
+// k take that path?  host_query_run: launch (x = optional shard exchange) and wait; fills the outputs.
+bool host_query_ok(const sema_index *s, uint32_t k);
+int host_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const sema::Exchange *x,
+                   uint64_t *row_ids, float *scores, uint32_t *n_found);
 // api_batch.cu: nq device-resident queries (nq x dim dense); K3 when the shape allows, else K2 per query
 int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
                uint32_t *nf_d);
+// api_batch.cu: a stream of nq single-query scans (K2 each), consecutive launches chained (PDL);
+// x / seq: optional fused shard exchange, *seq advanced once per query
+int scan_stream(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+                uint32_t *nf_d, sema::Exchange *x, uint64_t *seq);
 
 }  // namespace sema_impl

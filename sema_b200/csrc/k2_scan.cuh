@@ -68,6 +68,16 @@ struct ScanParams {
     uint32_t ld4;           // row stride in float4
     uint32_t k;
     uint32_t row_base;      // global id of local row 0
+    // TMA variant only: dynamic tile scheduler.  Tiles gridDim.x, gridDim.x + 1, ... are claimed
+    // with atomicAdd on *work_ctr (each block's first tile is static: blockIdx.x); the last block
+    // resets the counter.  Consecutive launches alternate between two counters because a launch
+    // chained with programmatic dependent launch starts scanning while its predecessor still merges.
+    unsigned int *work_ctr;
+    // Host-visible completion (sema_index_search with host buffers): res_* then point into mapped
+    // pinned host memory and the last block stores host_seq to *host_flag (release.sys) after the
+    // results, so the host can poll instead of issuing a D2H copy and a stream synchronise.
+    uint64_t *host_flag;
+    uint64_t host_seq;
     Exchange x;             // sharded mode (world > 1): fused peer exchange + global merge
 };
 
@@ -252,7 +262,15 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
     if (warp == 0) {
         emit_results<M, METRIC>(top, k, p.out_keys, p.res_ids, p.res_scores, p.res_nfound, lane);
         if (timed_out && p.res_nfound && lane == 0) *p.res_nfound = 0xffffffffu;   // host reports the failure
-        if (lane == 0) *p.ticket = 0;
+        if (lane == 0) {
+            *p.ticket = 0;
+            if (p.work_ctr) *p.work_ctr = 0;   // every block has stopped claiming tiles (all passed the ticket)
+        }
+        if (p.host_flag) {
+            __threadfence_system();            // each lane's result stores reach the host before the flag
+            __syncwarp();
+            if (lane == 0) st_release_sys(p.host_flag, p.host_seq);
+        }
     }
 }
 

@@ -7,6 +7,8 @@
 // parallelism no longer depends on registers or occupancy: TMA_STAGES * tile bytes are in flight
 // per SM.  Measured equal to the LDG kernel on large corpora (both sit at the HBM ceiling) and
 // ~3 % faster around 1M rows; default for dim 384 and 768 (sema_index_set_scan_variant selects).
+// Tiles are claimed dynamically and consecutive launches can be chained with programmatic
+// dependent launch (query streams: sema_index_search_stream_device), see the kernel comment.
 #pragma once
 #include "k2_scan.cuh"
 #include "ptx.cuh"
@@ -25,9 +27,31 @@ __host__ __device__ constexpr int tma_stage_bytes() { return tma_tile_rows<NV>()
 template <int NV>
 __host__ __device__ constexpr int tma_smem_bytes() { return TMA_STAGES * tma_stage_bytes<NV>() + 256; }
 
-template <int NV, int M, int METRIC>
+// The query itself as a kernel parameter (host-query entry points): it travels with the launch,
+// no H2D copy precedes the kernel.  QueryArg<0> is the placeholder of the device-pointer variant.
+template <int NV>
+struct QueryArg { float4 v[NV * 32]; };
+template <>
+struct QueryArg<0> { uint32_t unused; };
+
+constexpr uint32_t TMA_NO_TILE = 0xffffffffu;
+
+// Programmatic dependent launch: a launch carrying the programmatic-stream-serialization attribute
+// may start once every block of its predecessor has executed launch_dependents (or exited);
+// griddepcontrol.wait then blocks until the predecessor has completed and its writes are visible.
+// Both are no-ops in a launch without the attribute / without a dependent.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Tiles are scheduled dynamically: a block's first tile is blockIdx.x, every further one is claimed
+// with an atomicAdd on *p.work_ctr (two claims in flight per block, so the ~1 us round trip never
+// stalls the ring).  The tile index reaches the consumers through tile_of[stage], published before
+// the producer's arrive.expect_tx; TMA_NO_TILE marks the end.  With back-to-back launches chained
+// by programmatic dependent launch, a block that starts late (its SM was still running the
+// predecessor's last-block merge / shard exchange) simply claims fewer tiles.
+template <int NV, int M, int METRIC, bool QP>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-scan_topk_tma_kernel(const ScanParams p)
+scan_topk_tma_kernel(const __grid_constant__ ScanParams p, const __grid_constant__ QueryArg<QP ? NV : 0> qa)
 {
     using namespace ptx;
     constexpr int TMA_TILE_ROWS = tma_tile_rows<NV>();
@@ -37,13 +61,17 @@ scan_topk_tma_kernel(const ScanParams p)
     uint64_t *full = reinterpret_cast<uint64_t *>(tsm + TMA_STAGES * STAGE);
     uint64_t *empty = full + TMA_STAGES;
     __shared__ uint64_t sm_keys[TMA_CONSUMER_WARPS * 32 * M];
+    __shared__ uint32_t tile_of[TMA_STAGES];
     __shared__ bool is_last;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = p.n;
     const int k = (int)p.k;
-    const uint64_t bound = p.bound ? *p.bound : ~0ull;
     const uint32_t n_tiles = (n + TMA_TILE_ROWS - 1) / TMA_TILE_ROWS;
+
+    // the producer's first claim goes out before anything else: its latency overlaps the set-up
+    uint32_t c0 = blockIdx.x, c1 = 0;
+    if (warp == TMA_CONSUMER_WARPS && lane == 0) c1 = atomicAdd(p.work_ctr, 1u) + gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TMA_CONSUMER_WARPS); }
@@ -55,27 +83,50 @@ scan_topk_tma_kernel(const ScanParams p)
     top.init();
 
     if (warp == TMA_CONSUMER_WARPS) {
-        // ===== producer: tiles blockIdx.x, blockIdx.x + gridDim.x, ... =====
+        // ===== producer =====
         uint32_t stage = 0, phase = 0;
-        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        auto issue = [&](uint32_t t) {
             const uint32_t rows = min((uint32_t)TMA_TILE_ROWS, n - t * TMA_TILE_ROWS);
             const uint32_t bytes = rows * NV * 32 * 16;
             mbar_wait(&empty[stage], phase ^ 1);
+            if (lane == 0) tile_of[stage] = t;
+            __syncwarp();
             mbar_expect_tx(&full[stage], bytes);
             bulk_g2s(tsm + stage * STAGE, p.X + (size_t)t * TMA_TILE_ROWS * p.ld4, bytes, &full[stage]);
             if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
+        };
+        for (;;) {
+            uint32_t t = __shfl_sync(FULL, c0, 0);
+            if (t >= n_tiles) break;
+            if (lane == 0) c0 = atomicAdd(p.work_ctr, 1u) + gridDim.x;
+            issue(t);
+            t = __shfl_sync(FULL, c1, 0);
+            if (t >= n_tiles) break;
+            if (lane == 0) c1 = atomicAdd(p.work_ctr, 1u) + gridDim.x;
+            issue(t);
+        }
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) {
+            tile_of[stage] = TMA_NO_TILE;
+            mbar_arrive(&full[stage]);     // completes the phase: no bytes expected
         }
         __syncwarp();
     } else {
         // ===== consumers: warp w owns rows w*R .. w*R+R-1 of every tile =====
+        const uint64_t bound = p.bound ? *p.bound : ~0ull;
         float4 qv[NV];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) qv[v] = reinterpret_cast<const float4 *>(p.q)[v * 32 + lane];
+        for (int v = 0; v < NV; ++v) {
+            if constexpr (QP) qv[v] = qa.v[v * 32 + lane];
+            else qv[v] = reinterpret_cast<const float4 *>(p.q)[v * 32 + lane];
+        }
         const int my_r = row_of_lane<R>(lane);
         const bool rep = (lane & (32 / R - 1)) == 0;
         uint32_t stage = 0, phase = 0;
-        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (;;) {
             mbar_wait(&full[stage], phase);
+            const uint32_t t = *reinterpret_cast<volatile uint32_t *>(&tile_of[stage]);
+            if (t == TMA_NO_TILE) break;
             const float4 *tile = reinterpret_cast<const float4 *>(tsm + stage * STAGE) + (size_t)warp * R * NV * 32 + lane;
             float acc[R];
 #pragma unroll
@@ -94,6 +145,12 @@ scan_topk_tma_kernel(const ScanParams p)
             if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
         }
     }
+
+    // Everything below touches state shared with the previous launch on the stream (partials,
+    // ticket, result buffers, exchange slots): wait for it to have completed, then let the next
+    // launch start scanning on the SMs this grid's blocks leave.
+    griddep_wait();
+    griddep_launch_dependents();
 
     // ---- block merge over the 8 consumer warps (the producer holds no list), last-block merge,
     // ---- optional shard exchange, result emission — shared with scan_topk_kernel

@@ -134,6 +134,13 @@ class GpuIndex:
         check(self._L.sema_index_search(self._h, _ptr(q), k, _ptr(ids), _ptr(sc), C.byref(nf)))
         return nf.value
 
+    def search_ptr(self, q_ptr: C.c_void_p, k: int, ids_ptr: C.c_void_p, sc_ptr: C.c_void_p) -> int:
+        """sema_index_search on pre-built ctypes pointers (host buffers): the binding adds nothing but
+        the foreign call itself; returns n_found."""
+        nf = C.c_uint32()
+        check(self._L.sema_index_search(self._h, q_ptr, k, ids_ptr, sc_ptr, C.byref(nf)))
+        return nf.value
+
     def search_batch(self, Q: np.ndarray, k: int):
         """-> (row_ids uint64[nq,k], scores float32[nq,k], n_found uint32[nq])."""
         Q = np.ascontiguousarray(Q, dtype=np.float32)
@@ -150,6 +157,13 @@ class GpuIndex:
                             nfound_ptr: int) -> None:
         check(self._L.sema_index_search_batch_device(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(ids_ptr),
                                                      C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))
+
+    def search_stream_device(self, q_ptr: int, nq: int, k: int, ids_ptr: int, scores_ptr: int,
+                             nfound_ptr: int) -> None:
+        """A stream of nq independent single-query scans (K2 each, consecutive launches chained with
+        programmatic dependent launch); device pointers, results nq x k, nothing synchronises."""
+        check(self._L.sema_index_search_stream_device(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(ids_ptr),
+                                                      C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))
 
     def set_normalize_queries(self, on: bool) -> int:
         """Apply the reference's normalise tail (K1) to host queries before scanning."""
@@ -274,6 +288,17 @@ class ShardGroup:
         check(self._L.sema_shard_group_search(self._g, _ptr(q), k, _ptr(ids), _ptr(sc), C.byref(nf)))
         return nf.value
 
+    def search_ptr(self, q_ptr: C.c_void_p, k: int, ids_ptr: C.c_void_p, sc_ptr: C.c_void_p) -> int:
+        nf = C.c_uint32()
+        check(self._L.sema_shard_group_search(self._g, q_ptr, k, ids_ptr, sc_ptr, C.byref(nf)))
+        return nf.value
+
     def search_device(self, q_ptr: int, k: int, ids_ptr: int, scores_ptr: int, nfound_ptr: int) -> None:
         check(self._L.sema_shard_group_search_device(self._g, C.c_void_p(q_ptr), k, C.c_void_p(ids_ptr),
                                                      C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))
+
+    def search_stream_device(self, q_ptr: int, nq: int, k: int, ids_ptr: int, scores_ptr: int,
+                             nfound_ptr: int) -> None:
+        """nq group searches issued back to back (every rank: the same queries in the same order)."""
+        check(self._L.sema_shard_group_search_stream_device(self._g, C.c_void_p(q_ptr), nq, k, C.c_void_p(ids_ptr),
+                                                            C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))

@@ -717,3 +717,119 @@ def test_k3_cascade_uses_bf16x3_stage_for_many_dense_queries(sema, oracle_c):
     r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
     for i in range(16):
         O.check_parity(ids[i], sc[i], r_ids[i], r_sc[i])
+
+
+# ---------------------------------------------------------------- query streams (chained K2 launches) and the host-query path
+def _stream_search(sema, idx, Q, k, group=None):
+    import torch
+    dev = torch.device("cuda", idx.device)
+    nq = len(Q)
+    Qd = torch.from_numpy(np.ascontiguousarray(Q)).to(dev)
+    ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    sc = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    nf = torch.zeros(nq, dtype=torch.int32, device=dev)
+    idx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        (group or idx).search_stream_device(Qd.data_ptr(), nq, k, ids.data_ptr(), sc.data_ptr(), nf.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        idx.set_stream(None)
+    return ids.cpu().numpy().astype(np.uint64), sc.cpu().numpy(), nf.cpu().numpy()
+
+
+STREAM_CASES = [
+    # n, d, k, nq, metric
+    (1, 384, 10, 3, 0), (31, 384, 10, 5, 0), (33, 384, 50, 7, 1), (4737, 384, 10, 40, 0), (4737, 768, 100, 9, 0),
+    (150001, 384, 10, 64, 0), (150001, 384, 128, 6, 1), (60000, 768, 10, 33, 0),
+    (3000, 130, 10, 6, 0),      # generic kernel: the stream is not chained
+    (6000, 384, 300, 3, 0),     # k > 128: multi-pass launches are never chained
+]
+
+
+@pytest.mark.parametrize("n,d,k,nq,metric", STREAM_CASES)
+def test_query_stream_matches_oracle(sema, oracle_c, n, d, k, nq, metric):
+    """sema_index_search_stream_device: nq scans chained with programmatic dependent launch; every
+    query's result must be the oracle's (and therefore the one-query-per-call result)."""
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n, metric=metric) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = _stream_search(sema, idx, Q, k)
+        for i in range(nq):
+            r_ids, r_sc = oracle_c.scan(X, Q[i], k, metric)
+            assert nf[i] == len(r_ids) == min(k, n)
+            O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+            one_ids, one_sc = idx.search(Q[i], k)
+            assert np.array_equal(one_ids, ids[i, :nf[i]]) and np.array_equal(one_sc, sc[i, :nf[i]])
+
+
+def test_query_stream_chained_equals_unchained_bitwise(sema):
+    # the dynamic tile scheduler changes which block scans which tile, never the result
+    n, d, k, nq = 300007, 384, 10, 200
+    with sema.GpuIndex(d, n) as idx:
+        idx.append_synthetic(seed=1, row0=0, n=n, normalize=True)
+        Q = _unit(2, nq, d)
+        a = _stream_search(sema, idx, Q, k)
+        idx.set_scan_variant(600)              # unchained
+        b = _stream_search(sema, idx, Q, k)
+        idx.set_scan_variant(601)
+        idx.set_scan_variant(2)                # register-fed kernel, static schedule
+        c = _stream_search(sema, idx, Q, k)
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
+def test_query_stream_with_nulls_and_tombstones(sema, oracle_c):
+    n, d, k, nq = 20011, 384, 10, 12
+    X = _unit(1, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::7] = 0
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, valid=valid, normalize=False)
+        dead = np.arange(1, n, 11, dtype=np.uint64)
+        idx.tombstone(dead)
+        valid[dead] = 0
+        ids, sc, nf = _stream_search(sema, idx, Q, k)
+        for i in range(nq):
+            r_ids, r_sc = oracle_c.scan(X, Q[i], k, 0, valid)
+            O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+
+
+def test_shard_group_stream_world1(sema, oracle_c):
+    n, d, k, nq = 40000, 384, 10, 25
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.set_row_base(1_000_000)
+        idx.append(X, normalize=False)
+        g = sema.ShardGroup(idx, 1, 0)
+        try:
+            ids, sc, nf = _stream_search(sema, idx, Q, k, group=g)
+            for i in range(nq):
+                r_ids, r_sc = oracle_c.scan(X, Q[i], k, id_base=1_000_000)
+                O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+            one_ids, _ = g.search(Q[3], k)          # host call after a stream: sequence numbers stay in step
+            assert np.array_equal(one_ids, ids[3, :nf[3]])
+        finally:
+            g.close()
+
+
+@pytest.mark.parametrize("d,k", [(384, 10), (384, 50), (384, 128), (768, 100)])
+def test_host_query_path_equals_staged_path(sema, oracle_c, d, k):
+    """sema_index_search: query by kernel parameter + results to mapped host memory (default) against
+    the staged H2D / D2H path, many calls in a row (completion-flag sequencing)."""
+    n = 30011
+    X = _unit(1, n, d)
+    Q = _unit(2, 40, d)
+    for metric in (0, 1):
+        with sema.GpuIndex(d, n, metric=metric) as idx:
+            idx.append(X, normalize=False)
+            fast = [idx.search(q, k) for q in Q]
+            idx.set_scan_variant(500)
+            slow = [idx.search(q, k) for q in Q]
+            idx.set_scan_variant(501)
+            for (a, b), (c, e), q in zip(fast, slow, Q):
+                assert np.array_equal(a, c) and np.array_equal(b, e)
+            r_ids, r_sc = oracle_c.scan(X, Q[7], k, metric)
+            O.check_parity(fast[7][0], fast[7][1], r_ids, r_sc)
