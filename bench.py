@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--variant", type=int, default=-1, help="K2 kernel variant (tuning)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused = P2P stores + merge inside K2's last block; nccl = all-gather + K4")
-    ap.add_argument("--workload", default="single", choices=["single", "batch", "ingest", "config1"],
+    ap.add_argument("--workload", default="single", choices=["single", "batch", "ingest", "config1", "pool"],
                     help="single = headline single-query scan (K2); batch = BASELINE config 3, nq-query batches (K3); "
                          "ingest = BASELINE config 4/5 style streaming ingest (K1) interleaved with queries; "
                          "config1 = ~10k-chunk synthetic markdown corpus through the StorageManager boundary")
@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--pool-texts", type=int, default=4096, help="texts per step (--workload pool)")
+    ap.add_argument("--pool-full-mask", action="store_true", help="--workload pool: every token attended")
     ap.add_argument("--no-stream", action="store_true", help="timed region: one search call per query instead of one query stream")
     ap.add_argument("--no-chain", action="store_true", help="query stream without programmatic dependent launch (comparison)")
     ap.add_argument("--staged-host-path", action="store_true", help="e2e through the staged H2D / D2H path (comparison)")
@@ -298,6 +300,64 @@ def run_batch(a):
                 "path": "sema_index_search_batch (C ABI) with host buffers"},
         "gpu_launches": int(launches), "clocks": clk.summary(), "verified_against_k2": ok,
         "auto_mode_cascade": auto,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_pool(a):
+    """Kernel K0 (the step before the path): mean_pool of src/semantic/embeddings.rs:61-91 fused with the
+    append, for batches of texts whose token embeddings are already on the device.  One step pools and
+    appends `--pool-texts` texts of seq_len 256 (the reference's MAX_LENGTH) x dim."""
+    import torch
+
+    import sema_b200
+    from oracle import c_oracle
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:0")
+    n, seq, d = a.pool_texts, 256, a.dim
+    g = torch.Generator(device=dev).manual_seed(1)
+    tok = torch.randn((n, seq, d), generator=g, dtype=torch.float32, device=dev)
+    lens = torch.randint(8, seq + 1, (n,), generator=g, device=dev)
+    mask = (torch.arange(seq, device=dev)[None, :] < lens[:, None]).to(torch.float32).contiguous()
+    if a.pool_full_mask:
+        mask.fill_(1.0)
+    idx = sema_b200.GpuIndex(d, n * (a.steps + a.warmup + 1), device=0)
+    for _ in range(a.warmup):
+        idx.append_pooled_device(tok.data_ptr(), mask.data_ptr(), n, seq, None, skip_masked=True)
+    torch.cuda.synchronize()
+    l0 = idx.launch_count
+    with ClockSampler(0) as clk:
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            idx.append_pooled_device(tok.data_ptr(), mask.data_ptr(), n, seq, None, skip_masked=True)   # returns when the rows are visible
+        dt = time.perf_counter() - t0
+    launches = idx.launch_count - l0
+    # parity spot check on the first 64 texts of the last batch
+    first = len(idx) - n
+    got = idx.read_rows(first, 64)
+    want = c_oracle.mean_pool(tok[:64].cpu().numpy(), mask[:64].cpu().numpy())
+    read_bytes = float(mask.sum().item()) * d * 4          # rows of attended tokens: what K0 has to read
+    ms = dt * 1e3 / a.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    line = {
+        "metric": f"mean_pool_append_texts_per_s_seq{seq}x{d}_fp32", "value": n / (ms * 1e-3), "unit": "texts/s",
+        "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{n} texts x {seq} tokens x {d} fp32 token embeddings on the device, attention lengths uniform in [8, {seq}]"
+                               + (" (full masks)" if a.pool_full_mask else "") + ", mean_pool + normalise + append per step (K0 + K1 bookkeeping)",
+                   "timing": "host wall clock around sema_index_append_pooled_device (synchronous: rows visible on return)",
+                   "l2_flush": f"none needed: each step reads {read_bytes / 1e9:.2f} GB"},
+        "roofline": {"bound": "hbm", "achieved": read_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": read_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": read_bytes,
+                     "kernel": "pool_kernel (K0)", "note": "algorithmic bytes = attended tokens x dim x 4 (padding rows are skipped)"},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "verified": bool(np.array_equal(got, want)),
     }
     print(json.dumps(line), flush=True)
 
@@ -701,6 +761,8 @@ def main():
         run_ingest(a)
     elif a.workload == "config1":
         run_config1(a)
+    elif a.workload == "pool":
+        run_pool(a)
     else:
         run_ours(a)
 

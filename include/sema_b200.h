@@ -79,6 +79,28 @@ int sema_index_append_device(sema_index *idx, const float *rows_dev, uint64_t n,
 int sema_index_append_synthetic(sema_index *idx, uint64_t seed, uint64_t synth_row0, uint64_t n,
                                 int normalize, uint64_t *first_row);
 
+/* ---- the step before the path: mean pooling (kernel K0) ----------------------
+ * Replaces mean_pool (src/semantic/embeddings.rs:61-91), which turns the embedder's
+ * last_hidden_state into the vector that is stored (:27-59 -> lance_indexer.rs:63-71) or used as
+ * the query (lance_indexer.rs:114-118): pooled[j] = sum_i tokens[i][j]*mask[i] / sum_i mask[i],
+ * then the L2 normalise tail.  tokens: n x seq_len x dim fp32 (the reference runs n = 1,
+ * seq_len = MAX_LENGTH = 256, :7); mask: n x seq_len fp32 (attention_mask_f32, :38-46).  All sums
+ * keep the reference's order (i ascending, j ascending, multiply then add), so the output is
+ * bit-identical to it.  skip_masked != 0 does not read the rows of tokens whose mask is exactly 0
+ * (padding) — identical results for finite inputs, less HBM traffic.  out: n x dim dense.
+ * The _device variant enqueues on the query stream and does not synchronise. */
+int sema_mean_pool(sema_index *idx, const float *tokens, const float *mask, uint64_t n,
+                   uint32_t seq_len, int skip_masked, float *out);
+int sema_mean_pool_device(sema_index *idx, const float *tokens_dev, const float *mask_dev, uint64_t n,
+                          uint32_t seq_len, int skip_masked, float *out_dev);
+/* mean_pool fused with the append: K0 writes the pooled, normalised rows straight into their final
+ * place in the matrix (no intermediate n x dim buffer), then the column bookkeeping of
+ * sema_index_append_device runs in place.  valid_dev: nullable validity bytes (0 = the embedding
+ * failed, lance_indexer.rs:66-70).  Rows are visible when the call returns. */
+int sema_index_append_pooled_device(sema_index *idx, const float *tokens_dev, const float *mask_dev,
+                                    uint64_t n, uint32_t seq_len, const uint8_t *valid_dev,
+                                    int skip_masked, uint64_t *first_row);
+
 /* Replaces remove_file_chunks' `table.delete(predicate)`
  * (src/storage/lance_indexer.rs:234-250): the listed local rows stop matching. */
 int sema_index_tombstone(sema_index *idx, const uint64_t *rows, uint64_t n);

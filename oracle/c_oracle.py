@@ -36,6 +36,8 @@ def lib():
                                  C.POINTER(C.c_uint8), C.POINTER(C.c_uint32))
         L.sema_oracle_normalize.argtypes = [f32p, C.c_uint64, C.c_uint32]
         L.sema_oracle_normalize.restype = None
+        L.sema_oracle_mean_pool.argtypes = [f32p, f32p, C.c_uint64, C.c_uint32, C.c_uint32, f32p]
+        L.sema_oracle_mean_pool.restype = None
         L.sema_oracle_synth.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
         L.sema_oracle_synth.restype = None
         L.sema_oracle_scan.argtypes = [f32p, C.c_uint64, C.c_uint32, C.c_uint64, u8p, f32p,
@@ -70,6 +72,15 @@ def normalize(rows: np.ndarray) -> np.ndarray:
     n, d = x.shape
     lib().sema_oracle_normalize(_p(x, C.c_float), n, d)
     return x
+
+
+def mean_pool(tokens: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    tokens = np.ascontiguousarray(tokens, dtype=np.float32)
+    mask = np.ascontiguousarray(mask, dtype=np.float32)
+    n, seq, hidden = tokens.shape
+    out = np.empty((n, hidden), dtype=np.float32)
+    lib().sema_oracle_mean_pool(_p(tokens, C.c_float), _p(mask, C.c_float), n, seq, hidden, _p(out, C.c_float))
+    return out
 
 
 def synth(seed: int, row0: int, n: int, d: int, out: np.ndarray | None = None) -> np.ndarray:

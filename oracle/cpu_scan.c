@@ -13,6 +13,7 @@
  * the published behaviour of that engine at the reference's own call sites:
  *
  *   - normalise          src/semantic/embeddings.rs:83-88
+ *   - mean_pool          src/semantic/embeddings.rs:61-91
  *   - nullable vector column / row packing
  *                        src/storage/lance_indexer.rs:41-45, 59-76
  *   - flat exact KNN     src/storage/lance_indexer.rs:121-126
@@ -56,6 +57,40 @@ void sema_oracle_normalize(float *rows, uint64_t n, uint32_t d)
             for (uint32_t j = 0; j < d; ++j) x[j] = x[j] / norm;
         }
     }
+}
+
+/* ------------------------------------------------------------------------- */
+/* mean_pool — src/semantic/embeddings.rs:61-91 (the step that produces every  */
+/* stored vector and every query vector):                                     */
+/*   for i in 0..seq_len { mask_sum += mask[i];                                */
+/*       for j in 0..hidden { pooled[j] += token_embeddings[[0,i,j]] * mask[i] } } */
+/*   if mask_sum > 0.0 { pooled /= mask_sum }   then the normalise tail above. */
+/* Sequential f32 sums over i (per column) and over j (norm), multiply then    */
+/* add (no FMA: -ffp-contract=off).  n texts are independent.                  */
+/* ------------------------------------------------------------------------- */
+void sema_oracle_mean_pool(const float *tokens, const float *mask, uint64_t n, uint32_t seq,
+                           uint32_t hidden, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < (int64_t)n; ++t) {
+        const float *tok = tokens + (uint64_t)t * seq * hidden;
+        const float *m = mask + (uint64_t)t * seq;
+        float *pooled = out + (uint64_t)t * hidden;
+        for (uint32_t j = 0; j < hidden; ++j) pooled[j] = 0.0f;
+        volatile float mask_sum = 0.0f;
+        for (uint32_t i = 0; i < seq; ++i) {
+            const float mv = m[i];
+            mask_sum = mask_sum + mv;
+            for (uint32_t j = 0; j < hidden; ++j) {
+                float p = tok[(uint64_t)i * hidden + j] * mv;
+                pooled[j] = pooled[j] + p;
+            }
+        }
+        const float ms = mask_sum;
+        if (ms > 0.0f)
+            for (uint32_t j = 0; j < hidden; ++j) pooled[j] = pooled[j] / ms;
+    }
+    sema_oracle_normalize(out, n, hidden);
 }
 
 /* ------------------------------------------------------------------------- */

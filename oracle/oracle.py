@@ -11,6 +11,7 @@ lance 1.0.1 -> lance-index / lance-linalg 1.0.1, ``Cargo.lock:4258-4259,
 The functions below restate the behaviour at the reference's call sites:
 
 * :func:`normalize`  — ``src/semantic/embeddings.rs:83-88``
+* :func:`mean_pool`  — ``src/semantic/embeddings.rs:61-91``
 * :func:`scan`       — ``src/storage/lance_indexer.rs:121-126`` (LanceDB flat
   exact KNN, default metric squared L2, ascending ``_distance``, ``limit`` rows,
   null vectors skipped) and its dot/cosine twin on unit rows
@@ -52,6 +53,26 @@ def normalize(rows: np.ndarray) -> np.ndarray:
     nz = norm > 0
     x[nz] = x[nz] / norm[nz, None]
     return x
+
+
+def mean_pool(tokens: np.ndarray, mask: np.ndarray) -> np.ndarray:
+    """``mean_pool`` — ``src/semantic/embeddings.rs:61-91`` for n texts at once.
+
+    tokens [n, seq, hidden] f32, mask [n, seq] f32.  ``pooled[j] += tokens[i][j] * mask[i]`` with
+    i ascending (sequential f32, multiply then add), ``mask_sum`` likewise; divide by ``mask_sum``
+    iff it is > 0; then :func:`normalize`.
+    """
+    tokens = np.asarray(tokens, dtype=np.float32)
+    mask = np.asarray(mask, dtype=np.float32)
+    n, seq, hidden = tokens.shape
+    pooled = np.zeros((n, hidden), dtype=np.float32)
+    mask_sum = np.zeros(n, dtype=np.float32)
+    for i in range(seq):
+        mask_sum = mask_sum + mask[:, i]
+        pooled = pooled + tokens[:, i, :] * mask[:, i, None]
+    nz = mask_sum > 0
+    pooled[nz] = pooled[nz] / mask_sum[nz, None]
+    return normalize(pooled)
 
 
 def synth(seed: int, row0: int, n: int, d: int) -> np.ndarray:

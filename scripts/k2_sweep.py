@@ -1,4 +1,5 @@
-"""K2 latency sweep over corpus sizes (device-resident queries, CUDA events): fixed cost vs slope."""
+"""K2 sweep over corpus sizes (device-resident queries, CUDA events): per-call latency (one search
+call per query, launches serialised) and query-stream throughput (launches chained with PDL)."""
 import json
 import sys
 import os
@@ -37,6 +38,18 @@ for rows in [1000, 10_000, 100_000, 250_000, 500_000, 1_000_000, 2_000_000, 5_00
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        out.append((rows, v, ms))
-        print(f"rows={rows:>9} variant={v} {ms*1e3:9.1f} us  {rows*1536/ms/1e6:8.1f} GB/s", flush=True)
+        Qs = Qd[torch.arange(steps, device=dev) % 64].contiguous()
+        ids_s = torch.zeros((steps, k), dtype=torch.int64, device=dev)
+        sc_s = torch.zeros((steps, k), dtype=torch.float32, device=dev)
+        nf_s = torch.zeros(steps, dtype=torch.int32, device=dev)
+        idx.search_stream_device(Qs.data_ptr(), 20, k, ids_s.data_ptr(), sc_s.data_ptr(), nf_s.data_ptr())
+        torch.cuda.synchronize()
+        e0.record(stream)
+        idx.search_stream_device(Qs.data_ptr(), steps, k, ids_s.data_ptr(), sc_s.data_ptr(), nf_s.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_s = e0.elapsed_time(e1) / steps
+        out.append((rows, v, ms, ms_s))
+        print(f"rows={rows:>9} variant={v} per call {ms*1e3:9.1f} us {rows*1536/ms/1e6:8.1f} GB/s | "
+              f"query stream {ms_s*1e3:9.1f} us {rows*1536/ms_s/1e6:8.1f} GB/s", flush=True)
     idx.close()

@@ -39,6 +39,9 @@ SIGNATURES = {
     "sema_index_flush": (C.c_int, [_vp]),
     "sema_index_append_device": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_int, _u64p]),
     "sema_index_append_synthetic": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, _u64p]),
+    "sema_mean_pool": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_int, _vp]),
+    "sema_mean_pool_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, C.c_int, _vp]),
+    "sema_index_append_pooled_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp, C.c_int, _u64p]),
     "sema_index_tombstone": (C.c_int, [_vp, _vp, C.c_uint64]),
     "sema_index_compact": (C.c_int, [_vp, _vp, _u64p]),
     "sema_index_compact_keep": (C.c_int, [_vp, _vp, _vp, _u64p]),

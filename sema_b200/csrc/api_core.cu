@@ -284,6 +284,29 @@ int sema_index_append_device(sema_index *s, const float *rows_dev, uint64_t n,
     return sema_index_flush(s);
 }
 
+int sema_index_append_pooled_device(sema_index *s, const float *tokens_dev, const float *mask_dev, uint64_t n,
+                                    uint32_t seq_len, const uint8_t *valid_dev, int skip_masked, uint64_t *first_row)
+{
+    int rc = check_append(s, n);
+    if (rc) return rc;
+    if (n && (!tokens_dev || !mask_dev)) return fail(SEMA_ERR_INVALID, "null tokens / mask");
+    if (seq_len == 0) return fail(SEMA_ERR_INVALID, "seq_len = 0");
+    CK(cudaSetDevice(s->device));
+    const uint64_t first = s->n_rows;
+    if (first_row) *first_row = first;
+    if (n == 0) return SEMA_OK;
+    // K0 pools + normalises straight into the rows' final place; K1 (normalize = 0, in place) then
+    // only does the column's bookkeeping: null / non-finite rows -> NaN, validity bytes, max norm
+    float *dst = s->X + first * s->ld;
+    rc = launch_pool(s, s->ingest_stream, tokens_dev, mask_dev, n, seq_len, skip_masked, dst, s->ld);
+    if (rc) return rc;
+    rc = launch_ingest(s, dst, s->ld, first, n, valid_dev, 0, s->ld == s->dim);
+    if (rc) return rc;
+    rc = publish(s, n);
+    if (rc) return rc;
+    return sema_index_flush(s);
+}
+
 int sema_index_append_synthetic(sema_index *s, uint64_t seed, uint64_t synth_row0, uint64_t n,
                                 int normalize, uint64_t *first_row)
 {

@@ -3,7 +3,7 @@
 // struct sema_index owns the HBM layout (row-major fp32, row stride ld = round_up(dim,4) floats,
 // base 256-byte aligned by cudaMalloc, so every row is 16-byte aligned), the streams and the small
 // staging buffers.  api_core.cu: lifecycle, ingest (K1), tombstones, compaction, disk cache,
-// properties.  api_search.cu: K2 / K4 dispatch and the single-query entry points.  api_batch.cu:
+// properties.  api_pool.cu: K0 (mean pooling, the step before the path).  api_search.cu: K2 / K4 dispatch and the single-query entry points.  api_batch.cu:
 // K3 (planes, cluster launch, re-scoring, fallback) and the batched entry points.  api_shard.cu:
 // the fused peer exchange.  No CPU fallback exists: every compute entry point needs a CUDA device.
 #pragma once
@@ -124,6 +124,9 @@ namespace sema_impl {
 int poll_ingest(sema_index *s, bool wait);            // advance n_visible past completed ingests
 int ensure(void **p, size_t *cap, size_t need);       // grow a device scratch buffer
 int normalize_queries_dev(sema_index *s, float *q, uint64_t stride, uint32_t nq);   // K1 on queries, in place
+// api_pool.cu: kernel K0 (mean pooling + normalisation) for n texts on `stream`; out row stride out_ld floats
+int launch_pool(sema_index *s, cudaStream_t stream, const float *tokens_dev, const float *mask_dev, uint64_t n,
+                uint32_t seq_len, int skip_masked, float *out_dev, uint64_t out_ld);
 // api_search.cu: best k (any k <= SEMA_MAX_K) for one device-resident query; out_keys or res_* may be null
 int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys, uint64_t *res_ids,
                float *res_scores, uint32_t *res_nfound, const sema::Exchange *x = nullptr, unsigned flags = 0);

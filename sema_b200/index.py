@@ -89,6 +89,33 @@ class GpuIndex:
         check(self._L.sema_index_append_synthetic(self._h, seed, row0, n, int(normalize), C.byref(first)))
         return first.value
 
+    # -- the step before the path: mean pooling (K0) ------------------------------------
+    def mean_pool(self, tokens: np.ndarray, mask: np.ndarray, skip_masked: bool = False) -> np.ndarray:
+        """``mean_pool`` of ``src/semantic/embeddings.rs:61-91`` for n texts: tokens [n, seq, dim] fp32,
+        mask [n, seq] fp32 -> [n, dim] pooled + L2-normalised, bit-identical to the reference's sums."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.float32)
+        mask = np.ascontiguousarray(mask, dtype=np.float32)
+        if tokens.ndim != 3 or tokens.shape[2] != self.dim or mask.shape != tokens.shape[:2]:
+            raise ValueError(f"tokens must be [n, seq, {self.dim}] and mask [n, seq]; got {tokens.shape}, {mask.shape}")
+        out = np.empty((tokens.shape[0], self.dim), dtype=np.float32)
+        check(self._L.sema_mean_pool(self._h, _ptr(tokens), _ptr(mask), tokens.shape[0], tokens.shape[1],
+                                     int(skip_masked), _ptr(out)))
+        return out
+
+    def mean_pool_device(self, tokens_ptr: int, mask_ptr: int, n: int, seq_len: int, out_ptr: int,
+                         skip_masked: bool = False) -> None:
+        check(self._L.sema_mean_pool_device(self._h, C.c_void_p(tokens_ptr), C.c_void_p(mask_ptr), n, seq_len,
+                                            int(skip_masked), C.c_void_p(out_ptr)))
+
+    def append_pooled_device(self, tokens_ptr: int, mask_ptr: int, n: int, seq_len: int,
+                             valid_ptr: int | None = None, skip_masked: bool = False) -> int:
+        """mean_pool fused with the append (K0 writes straight into the matrix rows)."""
+        first = C.c_uint64()
+        check(self._L.sema_index_append_pooled_device(self._h, C.c_void_p(tokens_ptr), C.c_void_p(mask_ptr), n, seq_len,
+                                                      C.c_void_p(valid_ptr) if valid_ptr else None,
+                                                      int(skip_masked), C.byref(first)))
+        return first.value
+
     def tombstone(self, rows) -> None:
         r = np.ascontiguousarray(rows, dtype=np.uint64)
         check(self._L.sema_index_tombstone(self._h, _ptr(r), r.shape[0]))

@@ -28,7 +28,33 @@ CASES = [
 ]
 
 
+def pool_case():
+    """mean_pool (src/semantic/embeddings.rs:61-91): token embeddings with the reference's shapes
+    (seq_len 32 here to keep the fixture small; hidden 384), 0/1 attention masks of varying length,
+    one all-padding text (mask_sum = 0) and one all-zero text (norm = 0).  The fp32 answer is
+    cross-checked against a float64 evaluation of the same formula before it is written."""
+    n, seq, hidden = 6, 32, 384
+    tok = (O.synth(77, 0, n * seq, hidden) / np.float32(65536.0)).reshape(n, seq, hidden)
+    lens = [32, 17, 1, 0, 9, 25]
+    mask = np.zeros((n, seq), dtype=np.float32)
+    for t, ln in enumerate(lens):
+        mask[t, :ln] = 1.0
+    tok[4] = 0.0
+    out = O.mean_pool(tok, mask)
+    t64, m64 = tok.astype(np.float64), mask.astype(np.float64)
+    p64 = (t64 * m64[:, :, None]).sum(axis=1)
+    ms = m64.sum(axis=1)
+    p64[ms > 0] /= ms[ms > 0, None]
+    nr = np.sqrt((p64 * p64).sum(axis=1))
+    p64[nr > 0] /= nr[nr > 0, None]
+    assert np.allclose(out, p64, rtol=2e-5, atol=1e-7)
+    assert np.array_equal(out[3], np.zeros(hidden, np.float32)) and np.array_equal(out[4], np.zeros(hidden, np.float32))
+    np.savez_compressed(os.path.join(HERE, "pool384.npz"), tokens=tok, mask=mask, pooled=out, pooled64=p64)
+    print("wrote pool384", n, seq, hidden)
+
+
 def main():
+    pool_case()
     for name, n, d, nq, k, seed in CASES:
         raw = O.synth(seed, 0, n, d)
         valid = np.ones(n, dtype=np.uint8)

@@ -14,7 +14,7 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "g*.npz")))
 
 
 @pytest.fixture(scope="module")
@@ -833,3 +833,84 @@ def test_host_query_path_equals_staged_path(sema, oracle_c, d, k):
                 assert np.array_equal(a, c) and np.array_equal(b, e)
             r_ids, r_sc = oracle_c.scan(X, Q[7], k, metric)
             O.check_parity(fast[7][0], fast[7][1], r_ids, r_sc)
+
+
+# ---------------------------------------------------------------- K0: mean pooling (the step before the path)
+def _tokens(seed, n, seq, d):
+    return (O.synth(seed, 0, n * seq, d) / np.float32(65536.0)).reshape(n, seq, d)
+
+
+def _masks(n, seq, rng):
+    mask = np.zeros((n, seq), dtype=np.float32)
+    for t in range(n):
+        mask[t, :int(rng.integers(0, seq + 1))] = 1.0
+    return mask
+
+
+@pytest.mark.parametrize("n,seq,d", [(37, 256, 384), (5, 100, 768), (3, 7, 130), (300, 16, 384), (2, 256, 2048)])
+@pytest.mark.parametrize("skip", [False, True], ids=["readall", "skipmasked"])
+def test_k0_mean_pool_is_bit_identical_to_the_oracle(sema, oracle_c, n, seq, d, skip):
+    # src/semantic/embeddings.rs:61-91: every sum in the reference's order -> identical bits
+    rng = np.random.default_rng(5)
+    tok = _tokens(31, n, seq, d)
+    mask = _masks(n, seq, rng)
+    mask[0] = 1.0
+    if n > 2:
+        mask[1] = 0.0                       # all padding: mask_sum = 0
+        tok[2] = 0.0                        # all-zero text: norm = 0
+    want = oracle_c.mean_pool(tok, mask)
+    with sema.GpuIndex(d, 4) as idx:
+        got = idx.mean_pool(tok, mask, skip_masked=skip)
+    assert np.array_equal(got, want)
+    if n > 2:
+        assert not got[1].any() and not got[2].any()
+
+
+def test_k0_fractional_masks_and_golden_fixture(sema, oracle_c):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pool384.npz"))
+    with sema.GpuIndex(384, 4) as idx:
+        assert np.array_equal(idx.mean_pool(g["tokens"], g["mask"]), g["pooled"])
+        assert np.array_equal(idx.mean_pool(g["tokens"], g["mask"], skip_masked=True), g["pooled"])
+        tok = _tokens(8, 4, 19, 384)
+        mask = np.random.default_rng(3).random((4, 19)).astype(np.float32)      # the code multiplies by any value
+        assert np.array_equal(idx.mean_pool(tok, mask), oracle_c.mean_pool(tok, mask))
+
+
+def test_k0_pooled_append_and_pooled_query_end_to_end(sema, oracle_c):
+    """embed -> mean_pool -> store, and embed -> mean_pool -> search, all on the device: the stored rows
+    are the oracle's pooled vectors bit for bit and the search over them matches the oracle's scan."""
+    import torch
+    n, seq, d, k = 3000, 24, 384, 10
+    rng = np.random.default_rng(11)
+    tok = _tokens(41, n, seq, d)
+    mask = _masks(n, seq, rng)
+    mask[:, 0] = 1.0                                    # [CLS] is always attended
+    valid = np.ones(n, np.uint8)
+    valid[::13] = 0                                     # failed embeddings (lance_indexer.rs:66-70)
+    X = oracle_c.mean_pool(tok, mask)
+    qtok, qmask = _tokens(42, 4, seq, d), _masks(4, seq, rng)
+    qmask[:, 0] = 1.0
+    Q = oracle_c.mean_pool(qtok, qmask)
+    dev = torch.device("cuda:0")
+    tok_d, mask_d, valid_d = torch.from_numpy(tok).to(dev), torch.from_numpy(mask).to(dev), torch.from_numpy(valid).to(dev)
+    qtok_d, qmask_d = torch.from_numpy(qtok).to(dev), torch.from_numpy(qmask).to(dev)
+    Q_d = torch.zeros((4, d), dtype=torch.float32, device=dev)
+    ids = torch.zeros((4, k), dtype=torch.int64, device=dev)
+    sc = torch.zeros((4, k), dtype=torch.float32, device=dev)
+    nf = torch.zeros(4, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    with sema.GpuIndex(d, n + 10) as idx:
+        assert idx.append_pooled_device(tok_d.data_ptr(), mask_d.data_ptr(), n, seq, valid_d.data_ptr(), skip_masked=True) == 0
+        assert len(idx) == n and idx.visible == n
+        got = idx.read_rows(0, n)
+        live = valid != 0
+        assert np.array_equal(got[live], X[live]) and np.isnan(got[~live]).all()
+        idx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        idx.mean_pool_device(qtok_d.data_ptr(), qmask_d.data_ptr(), 4, seq, Q_d.data_ptr())
+        idx.search_stream_device(Q_d.data_ptr(), 4, k, ids.data_ptr(), sc.data_ptr(), nf.data_ptr())
+        torch.cuda.synchronize()
+        idx.set_stream(None)
+    assert np.array_equal(Q_d.cpu().numpy(), Q)
+    for i in range(4):
+        r_ids, r_sc = oracle_c.scan(X, Q[i], k, 0, valid)
+        O.check_parity(ids[i].cpu().numpy().astype(np.uint64), sc[i].cpu().numpy(), r_ids, r_sc)

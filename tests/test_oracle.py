@@ -11,7 +11,7 @@ import pytest
 
 from oracle import oracle as O
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "g*.npz")))
 
 
 def test_normalize_kat():
@@ -165,3 +165,54 @@ def test_check_parity_rejects_wrong_order():
     # a swap inside the tie tolerance is accepted
     sc_t = np.array([0.9, 0.500001, 0.5], np.float32)
     O.check_parity(np.array([1, 3, 2], np.uint64), sc_t, ids, sc_t)
+
+
+# ---------------------------------------------------------------- mean_pool (the step before the path)
+def _mean_pool_literal(tok, mask):
+    """Scalar transliteration of src/semantic/embeddings.rs:61-91, one text, np.float32 scalars."""
+    seq, hidden = tok.shape
+    pooled = [np.float32(0.0)] * hidden
+    mask_sum = np.float32(0.0)
+    for i in range(seq):
+        mv = np.float32(mask[i])
+        mask_sum = np.float32(mask_sum + mv)
+        for j in range(hidden):
+            pooled[j] = np.float32(pooled[j] + np.float32(tok[i, j] * mv))
+    if mask_sum > 0:
+        pooled = [np.float32(v / mask_sum) for v in pooled]
+    ss = np.float32(0.0)
+    for v in pooled:
+        ss = np.float32(ss + np.float32(v * v))
+    norm = np.float32(np.sqrt(ss))
+    if norm > 0:
+        pooled = [np.float32(v / norm) for v in pooled]
+    return np.array(pooled, dtype=np.float32)
+
+
+def test_mean_pool_kat():
+    # two tokens attended, one padded: pooled = mean of the attended rows, then unit norm
+    tok = np.array([[[3.0, 0.0], [0.0, 4.0], [100.0, 100.0]]], dtype=np.float32)
+    mask = np.array([[1.0, 1.0, 0.0]], dtype=np.float32)
+    out = O.mean_pool(tok, mask)
+    assert np.array_equal(out[0], np.array([1.5, 2.0], np.float32) / np.float32(2.5))
+    # an all-padding text: mask_sum = 0 -> no division, pooled = 0 -> norm = 0 -> stays zero
+    assert np.array_equal(O.mean_pool(tok, np.zeros((1, 3), np.float32))[0], np.zeros(2, np.float32))
+
+
+def test_mean_pool_vectorised_equals_literal_loop_and_c(oracle_c):
+    tok = (O.synth(9, 0, 3 * 11, 20) / np.float32(4096.0)).reshape(3, 11, 20)
+    mask = np.zeros((3, 11), dtype=np.float32)
+    mask[0, :11] = 1.0
+    mask[1, :4] = 1.0
+    mask[2, :7] = 0.5                       # the code multiplies by the mask value, whatever it is
+    got = O.mean_pool(tok, mask)
+    for t in range(3):
+        assert np.array_equal(got[t], _mean_pool_literal(tok[t], mask[t]))
+    assert np.array_equal(got, oracle_c.mean_pool(tok, mask))
+
+
+def test_mean_pool_golden_fixture(oracle_c):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pool384.npz"))
+    assert np.array_equal(O.mean_pool(g["tokens"], g["mask"]), g["pooled"])
+    assert np.array_equal(oracle_c.mean_pool(g["tokens"], g["mask"]), g["pooled"])
+    np.testing.assert_allclose(g["pooled"], g["pooled64"], rtol=2e-5, atol=1e-7)
