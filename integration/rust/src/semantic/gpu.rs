@@ -21,6 +21,8 @@ extern "C" {
                          n_found: *mut u32) -> c_int;
     fn sema_index_search_batch(idx: *mut SemaIndex, q: *const f32, nq: u32, k: u32, row_ids: *mut u64,
                                scores: *mut f32, n_found: *mut u32) -> c_int;
+    fn sema_mean_pool(idx: *mut SemaIndex, tokens: *const f32, mask: *const f32, n: u64, seq_len: u32,
+                      skip_masked: c_int, out: *mut f32) -> c_int;
     fn sema_index_size(idx: *const SemaIndex) -> u64;
     fn sema_index_save(idx: *mut SemaIndex, path: *const c_char) -> c_int;
     fn sema_index_load(path: *const c_char, device: c_int, capacity_rows: u64, out: *mut *mut SemaIndex) -> c_int;
@@ -79,6 +81,19 @@ impl GpuIndex {
         Ok((0..nq)
             .map(|i| (0..nf[i] as usize).map(|j| (ids[i * limit + j], sc[i * limit + j])).collect())
             .collect())
+    }
+
+    /// Drop-in for `mean_pool` (src/semantic/embeddings.rs:61-91) over n texts: tokens is the ONNX
+    /// last_hidden_state (n x seq_len x dim), mask the f32 attention mask (n x seq_len).  The GPU
+    /// keeps the reference's summation order, so the result is bit-identical to the CPU function.
+    pub fn mean_pool(&mut self, tokens: &[f32], mask: &[f32], seq_len: usize) -> anyhow::Result<Vec<f32>> {
+        let n = mask.len() / seq_len;
+        anyhow::ensure!(tokens.len() == n * seq_len * self.dim, "tokens / mask shape mismatch");
+        let mut out = vec![0f32; n * self.dim];
+        check(unsafe {
+            sema_mean_pool(self.raw, tokens.as_ptr(), mask.as_ptr(), n as u64, seq_len as u32, 1, out.as_mut_ptr())
+        })?;
+        Ok(out)
     }
 
     pub fn tombstone(&mut self, rows: &[u64]) -> anyhow::Result<()> {
