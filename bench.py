@@ -620,6 +620,7 @@ def run_ours(a):
         qh = [ctypes.c_void_p(Q[i].ctypes.data) for i in range(a.queries)]      # host pointers, built once
         ids_p, sc_p = ctypes.c_void_p(ids_h.ctypes.data), ctypes.c_void_p(sc_h.ctypes.data)
         e2e_ms = None
+        e2e_lat = None
         if a.staged_host_path:
             idx.set_scan_variant(500)
         if world == 1:
@@ -627,11 +628,18 @@ def run_ours(a):
             for i in range(min(a.warmup, 5)):
                 idx.search_ptr(qh[i % a.queries], k, ids_p, sc_p)
             torch.cuda.synchronize()
+            lat = np.empty(a.steps)
             t0 = time.perf_counter()
+            tp = t0
             for i in range(a.steps):
-                idx.search_ptr(qh[i % a.queries], k, ids_p, sc_p)
+                idx.search_ptr(qh[i % a.queries], k, ids_p, sc_p)      # synchronous: results are in ids_h / sc_h on return
+                tn = time.perf_counter()
+                lat[i] = tn - tp
+                tp = tn
             torch.cuda.synchronize()
             e2e_ms = (time.perf_counter() - t0) * 1e3
+            e2e_lat = {"median_ms": float(np.median(lat)) * 1e3, "p99_ms": float(np.percentile(lat, 99)) * 1e3,
+                       "max_ms": float(lat.max()) * 1e3}
         elif group is not None:
             for i in range(min(a.warmup, 5)):
                 group.search_ptr(qh[i % a.queries], k, ids_p, sc_p)
@@ -667,17 +675,25 @@ def run_ours(a):
         i = (a.steps - 1) % a.queries
         r_ids, r_sc = idx.search(Q[i], k)
         verified = bool(np.array_equal(ids_d.cpu().numpy().astype(np.uint64), r_ids))
+        if use_stream:                            # every result of the timed (chained) stream against a fresh host search
+            ids_stream = ids_s.cpu().numpy().astype(np.uint64)
+            for j in range(min(a.steps, a.queries, 8)):
+                verified &= bool(np.array_equal(ids_stream[j], idx.search(Q[j], k)[0]))
     elif not a.no_verify:
         # multi-rank: the fused result must equal the NCCL all-gather + K4 result, and every global
         # hit that lives on this rank must be this rank's own local hit with the same score
         from sema_b200.sharded import ShardedSearcher
         sh = ShardedSearcher(idx, dist, k)
         verified = True
+        ids_stream = ids_s.cpu().numpy().astype(np.uint64) if use_stream else None
+        sc_stream = sc_s.cpu().numpy() if use_stream else None
         for i in range(4):
             n_ids, n_sc = sh.search(Q[i])
             if group is not None:
                 f_ids, f_sc = group.search(Q[i], k)
                 verified &= bool(np.array_equal(f_ids, n_ids) and np.array_equal(f_sc, n_sc))
+            if use_stream and i < a.steps:        # query i of the timed (chained) stream was pool query i
+                verified &= bool(np.array_equal(ids_stream[i], n_ids) and np.array_equal(sc_stream[i], n_sc))
             l_ids, l_sc = idx.search(Q[i], k)
             mine = (n_ids >= lo) & (n_ids < hi)
             verified &= bool(set(n_ids[mine].tolist()) <= set(l_ids.tolist()))
@@ -733,7 +749,7 @@ def run_ours(a):
                     + ("" if world == 1 else ", which includes the top-k exchange and the global merge") + ")",
         },
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": ((a.dim + 3) // 4) * 16,
-                "d2h_bytes_per_step": 8 + 12 * k, "ms_per_step": e2e_ms / a.steps,
+                "d2h_bytes_per_step": 8 + 12 * k, "ms_per_step": e2e_ms / a.steps, "latency": e2e_lat,
                 "path": ("sema_index_search" if world == 1 else "sema_shard_group_search" if group is not None else "sharded.ShardedSearcher.search")
                         + " with host buffers: the query travels in the kernel parameters (these bytes), K2 (+ exchange + merge) stores"
                           " the result block into mapped host memory (these bytes), the call polls its completion flag"},

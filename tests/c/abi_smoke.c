@@ -67,6 +67,35 @@ int main(void)
     }
     for (int i = 1; i < 10; ++i)
         if (sc[i] > sc[i - 1]) return 1;
+    /* the host-query path (query in the kernel parameters, results through mapped host memory):
+     * an already normalised stored row, several calls in a row */
+    static float qn[DIM];
+    CHECK(sema_index_read_rows(idx, 77, 1, qn));
+    CHECK(sema_index_set_normalize_queries(idx, 0) == 0 ? SEMA_OK : SEMA_ERR_INVALID);
+    for (int rep = 0; rep < 3; ++rep) {
+        CHECK(sema_index_search(idx, qn, 10, ids, sc, &nf));
+        if (nf != 10 || ids[0] != 77 || fabsf(sc[0] - 1.0f) > 1e-5f) return 1;
+    }
+    /* mean_pool (kernel K0, src/semantic/embeddings.rs:61-91): 3 tokens, the last one padding */
+    {
+        static float tok[3 * DIM], pooled[DIM], want[DIM];
+        const float mask[3] = {1.0f, 1.0f, 0.0f};
+        for (int i = 0; i < 3 * DIM; ++i) tok[i] = rnd();
+        CHECK(sema_mean_pool(idx, tok, mask, 1, 3, /*skip_masked=*/1, pooled));
+        volatile float ss = 0.0f;
+        for (int j = 0; j < DIM; ++j) {
+            volatile float acc = 0.0f;
+            for (int i = 0; i < 3; ++i) { volatile float pr = tok[i * DIM + j] * mask[i]; acc = acc + pr; }
+            want[j] = acc / 2.0f;
+        }
+        for (int j = 0; j < DIM; ++j) { volatile float sq = want[j] * want[j]; ss = ss + sq; }
+        const float norm = sqrtf(ss);
+        for (int j = 0; j < DIM; ++j)
+            if (pooled[j] != want[j] / norm) {
+                fprintf(stderr, "mean_pool[%d] = %.9g, expected %.9g\n", j, pooled[j], want[j] / norm);
+                return 1;
+            }
+    }
     uint64_t dead = 1234;
     CHECK(sema_index_tombstone(idx, &dead, 1));
     CHECK(sema_index_search(idx, rows + (size_t)1234 * DIM, 10, ids, sc, &nf));
