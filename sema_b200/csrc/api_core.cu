@@ -187,7 +187,7 @@ int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metr
     CKD(cudaMemset(s->ticket, 0, 4 * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
     CKD(cudaMalloc(&s->max_norm2, sizeof(float)));
-    CKD(cudaMalloc(&s->qscratch, 65536 + 16));
+    CKD(cudaMalloc(&s->qscratch, 65536 + 32));
     CKD(cudaMemset(s->max_norm2, 0, sizeof(float)));
     CKD(cudaMalloc(&s->res_dev, res_bytes));
     CKD(cudaHostAlloc(&s->res_pin, res_bytes, cudaHostAllocPortable));

@@ -103,7 +103,7 @@ struct sema_index {
     int k3_kc16 = 1;                    // single-pass stage with k <= 10 keeps 16 candidates per list (0 = 32) — tuning
     int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
     int normalize_queries = 0;          // apply K1 to host queries before scanning
-    unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch]
+    unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch][K0 text counters: +8 query stream, +16 ingest stream]
     uint64_t k3_queries = 0, k3_fallbacks = 0, k3_cascaded = 0;
     float *sub_q = nullptr;             // cascade: the queries the single-pass stage could not prove, and their results
     uint64_t *sub_ids = nullptr;

@@ -15,16 +15,18 @@
 
 namespace sema {
 
-constexpr int POOL_MAX_THREADS = 1024;
+constexpr int POOL_MAX_THREADS = 512;   // keeps the register budget above what 16 loads in flight per thread need
 
-// One block per text (grid-stride).  Dynamic shared memory: (3 * seq + hidden) floats.
+// One block per text; texts are claimed from *next_text (atomicAdd, zeroed before the launch) by a
+// grid of exactly the resident blocks, so texts of different attended length balance out and no
+// second, partly filled wave exists.  Dynamic shared memory: (3 * seq + hidden) floats.
 // out: row stride out_ld floats; columns [hidden, out_ld) are written as zeros.
 // The tokens a text actually reads are first compacted into a list (index, mask value) — all of
 // them, or with skip_masked those whose mask is not 0 — so that the accumulation loop is branch-free
 // and unrolled with 16 independent loads in flight per thread (the adds stay in token order).
 __global__ void __launch_bounds__(POOL_MAX_THREADS)
 pool_kernel(const float *tokens, const float *mask, uint64_t n, uint32_t seq, uint32_t hidden, float *out,
-            uint64_t out_ld, int skip_masked)
+            uint64_t out_ld, int skip_masked, unsigned long long *next_text)
 {
     extern __shared__ float psm[];
     float *sm_mask = psm;                                          // [seq]   all mask values (mask_sum)
@@ -33,9 +35,14 @@ pool_kernel(const float *tokens, const float *mask, uint64_t n, uint32_t seq, ui
     float *sm_pool = psm + 3 * seq;                                // [hidden]
     __shared__ float sm_norm;
     __shared__ uint32_t sm_cnt;
+    __shared__ unsigned long long sm_text;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (uint64_t t = blockIdx.x; t < n; t += gridDim.x) {
+    for (;;) {
+        if (threadIdx.x == 0) sm_text = atomicAdd(next_text, 1ull);
+        __syncthreads();
+        const uint64_t t = sm_text;
+        if (t >= n) break;
         const float *tok = tokens + t * (uint64_t)seq * hidden;
         for (uint32_t i = threadIdx.x; i < seq; i += blockDim.x) sm_mask[i] = mask[t * seq + i];
         __syncthreads();
