@@ -914,3 +914,45 @@ def test_k0_pooled_append_and_pooled_query_end_to_end(sema, oracle_c):
     for i in range(4):
         r_ids, r_sc = oracle_c.scan(X, Q[i], k, 0, valid)
         O.check_parity(ids[i].cpu().numpy().astype(np.uint64), sc[i].cpu().numpy(), r_ids, r_sc)
+
+
+def test_query_stream_edge_cases(sema, oracle_c):
+    # empty index -> n_found = 0 for every query (lance_indexer.rs:108-111); a single query; k = 1; k > rows
+    d = 384
+    Q = _unit(2, 5, d)
+    with sema.GpuIndex(d, 100) as idx:
+        ids, sc, nf = _stream_search(sema, idx, Q, 10)
+        assert not nf.any()
+        g = sema.ShardGroup(idx, 1, 0)
+        try:
+            _, _, nf = _stream_search(sema, idx, Q, 10, group=g)      # an empty shard still runs the exchange
+            assert not nf.any()
+            X = _unit(1, 7, d)
+            idx.append(X, normalize=False)
+            ids, sc, nf = _stream_search(sema, idx, Q[:1], 1)
+            r_ids, r_sc = oracle_c.scan(X, Q[0], 1)
+            assert nf[0] == 1 and ids[0, 0] == r_ids[0]
+            ids, sc, nf = _stream_search(sema, idx, Q, 50, group=g)   # limit > rows: every row, ranked
+            for i in range(5):
+                r_ids, r_sc = oracle_c.scan(X, Q[i], 50)
+                assert nf[i] == 7
+                O.check_parity(ids[i, :7], sc[i, :7], r_ids, r_sc)
+        finally:
+            g.close()
+
+
+def test_query_stream_interleaved_with_appends_and_host_searches(sema, oracle_c):
+    # streams, host-query calls and appends alternate on one handle: counters, flags and snapshots stay consistent
+    d, k = 384, 10
+    X = _unit(1, 9000, d)
+    Q = _unit(2, 6, d)
+    with sema.GpuIndex(d, 9000) as idx:
+        for step, hi in enumerate((3000, 6000, 9000)):
+            idx.append(X[hi - 3000:hi], normalize=False)
+            ids, sc, nf = _stream_search(sema, idx, Q, k)
+            for i in range(6):
+                r_ids, r_sc = oracle_c.scan(X[:hi], Q[i], k)
+                O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+                h_ids, h_sc = idx.search(Q[i], k)
+                assert np.array_equal(h_ids, ids[i, :nf[i]]) and np.array_equal(h_sc, sc[i, :nf[i]])
+            assert idx.last_snapshot == hi
