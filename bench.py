@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--pool-texts", type=int, default=4096, help="texts per step (--workload pool)")
     ap.add_argument("--pool-full-mask", action="store_true", help="--workload pool: every token attended")
+    ap.add_argument("--growable", action="store_true", help="corpus in a growable (virtual-memory backed) index")
     ap.add_argument("--no-stream", action="store_true", help="timed region: one search call per query instead of one query stream")
     ap.add_argument("--no-chain", action="store_true", help="query stream without programmatic dependent launch (comparison)")
     ap.add_argument("--staged-host-path", action="store_true", help="e2e through the staged H2D / D2H path (comparison)")
@@ -525,7 +526,7 @@ def run_ours(a):
     # ---- corpus: rows [lo, hi) of the fixed synthetic corpus live on this GPU
     per = (a.rows + world - 1) // world
     lo, hi = min(rank * per, a.rows), min((rank + 1) * per, a.rows)
-    idx = sema_b200.GpuIndex(a.dim, max(hi - lo, 1), device=local)
+    idx = sema_b200.GpuIndex(a.dim, max(hi - lo, 1), device=local, growable=a.growable)
     idx.set_row_base(lo)
     idx.append_synthetic(seed=1, row0=lo, n=hi - lo, normalize=True)
     if a.variant >= 0:

@@ -49,6 +49,14 @@ typedef struct sema_index sema_index;
  * staging buffers.  metric is SEMA_METRIC_*. */
 int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metric,
                       sema_index **out);
+/* Growable variant — what the reference's table is (table.add appends without a declared size,
+ * src/storage/lance_indexer.rs:92-95): max_rows only reserves ADDRESS SPACE for the matrix (and the
+ * validity bytes, and K3's bf16 planes); physical HBM is mapped in 256 MB steps as rows are
+ * appended (CUDA virtual memory management), so the matrix stays contiguous for the scan kernels,
+ * never needs a realloc-and-copy, and an index that holds 10 k rows costs 256 MB whatever its
+ * max_rows.  Everything else behaves like sema_index_create; sema_index_capacity() = max_rows. */
+int sema_index_create_growable(int device, uint32_t dim, uint64_t max_rows, int metric,
+                               sema_index **out);
 int sema_index_destroy(sema_index *idx);
 
 /* ---- ingest (kernel K1) --------------------------------------------------

@@ -56,7 +56,9 @@ typedef int (*sema_embed_fn)(void *user, const char *text, float *out, uint32_t 
 
 /* StorageManager::new / LanceIndexer::new (src/storage/mod.rs:19-29): normalize != 0 applies
  * the mean_pool normalise tail (src/semantic/embeddings.rs:83-88) to stored rows and queries
- * on the device. */
+ * on the device.  The vector index is growable (sema_index_create_growable): capacity_rows bounds
+ * the address space only, 0 = no bound short of the 32-bit row ids — the reference's table has no
+ * declared size either. */
 int sema_store_create(int device, uint32_t dim, uint64_t capacity_rows, int normalize, sema_store **out);
 int sema_store_destroy(sema_store *st);
 int sema_store_set_embedder(sema_store *st, sema_embed_fn fn, void *user);

@@ -33,6 +33,7 @@ _vp = C.c_void_p
 # name -> (restype, argtypes); mirrors include/sema_b200.h one to one
 SIGNATURES = {
     "sema_index_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(_vp)]),
+    "sema_index_create_growable": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "sema_index_destroy": (C.c_int, [_vp]),
     "sema_index_append": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_int, _u64p]),
     "sema_index_append_async": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_int, _u64p]),

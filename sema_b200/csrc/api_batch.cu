@@ -27,14 +27,29 @@ int k3_sync_planes(sema_index *s, uint64_t n)
 {
     if (!s->planes) {
         const uint64_t tiles = (s->capacity + k3::TILE_N - 1) / k3::TILE_N;
-        cudaError_t e = cudaMalloc(&s->planes, (size_t)(tiles ? tiles : 1) * k3::tile_bytes((int)s->dim));
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            s->planes = nullptr;
-            s->planes_failed = true;  // not an error: the K2 loop serves the batch instead
-            return SEMA_ERR_NOMEM;
+        const size_t bytes = (size_t)(tiles ? tiles : 1) * k3::tile_bytes((int)s->dim);
+        if (s->growable) {
+            if (growbuf_reserve(s->gPlanes, s->device, bytes, (size_t)256 << 20) != SEMA_OK) {
+                s->planes_failed = true;
+                return SEMA_ERR_NOMEM;
+            }
+            s->planes = reinterpret_cast<unsigned char *>(s->gPlanes.base);
+        } else {
+            cudaError_t e = cudaMalloc(&s->planes, bytes);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                s->planes = nullptr;
+                s->planes_failed = true;  // not an error: the K2 loop serves the batch instead
+                return SEMA_ERR_NOMEM;
+            }
         }
         s->planes_rows = 0;
+    }
+    if (s->growable) {   // physical memory for the tiles that exist
+        const uint64_t tiles_n = (n + k3::TILE_N - 1) / k3::TILE_N;
+        int rc = growbuf_commit(s->gPlanes, (size_t)tiles_n * k3::tile_bytes((int)s->dim));
+        if (rc == SEMA_ERR_NOMEM) { s->planes_failed = true; return SEMA_ERR_NOMEM; }
+        if (rc) return rc;
     }
     if (s->planes_rows >= n) return SEMA_OK;
     const uint64_t begin = (s->planes_rows / k3::TILE_N) * k3::TILE_N;            // re-tile the partial last tile

@@ -105,6 +105,13 @@ int check_append(sema_index *s, uint64_t n)
                     (unsigned long long)n, (unsigned long long)s->capacity, (unsigned long long)s->n_rows);
     if ((uint64_t)s->row_base + s->n_rows + n > 0xfffffffeull)
         return fail(SEMA_ERR_CAPACITY, "global row ids must stay below 2^32-1");
+    if (s->growable && n) {   // back the new rows with physical memory (existing mappings are untouched: searches may be running)
+        CK(cudaSetDevice(s->device));
+        int rc = growbuf_commit(s->gX, (size_t)(s->n_rows + n) * s->ld * sizeof(float));
+        if (rc) return rc;
+        rc = growbuf_commit(s->gValid, (size_t)(s->n_rows + n));
+        if (rc) return rc;
+    }
     return SEMA_OK;
 }
 
@@ -138,7 +145,20 @@ int sema_host_free(void *p)
     return SEMA_OK;
 }
 
+static int create_impl(int device, uint32_t dim, uint64_t capacity_rows, int metric, bool growable, sema_index **out);
+
 int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metric, sema_index **out)
+{
+    return create_impl(device, dim, capacity_rows, metric, false, out);
+}
+
+int sema_index_create_growable(int device, uint32_t dim, uint64_t max_rows, int metric, sema_index **out)
+{
+    if (max_rows == 0) return fail(SEMA_ERR_INVALID, "max_rows = 0");
+    return create_impl(device, dim, max_rows, metric, true, out);
+}
+
+static int create_impl(int device, uint32_t dim, uint64_t capacity_rows, int metric, bool growable, sema_index **out)
 {
     if (!out) return fail(SEMA_ERR_INVALID, "null out");
     *out = nullptr;
@@ -176,8 +196,18 @@ int sema_index_create(int device, uint32_t dim, uint64_t capacity_rows, int metr
     CKD(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     CKD(cudaStreamCreateWithFlags(&s->ingest_stream, cudaStreamNonBlocking));
     s->stream = s->own_stream;
-    CKD(cudaMalloc(&s->X, xbytes));
-    CKD(cudaMalloc(&s->valid, capacity_rows ? capacity_rows : 1));
+    if (growable) {
+        s->growable = true;
+        // 256 MB steps for the matrix (the growth is amortised over ~170 k rows of dim 384), granularity-sized ones for the validity bytes
+        int rc_ = growbuf_reserve(s->gX, device, xbytes, (size_t)256 << 20);
+        if (rc_ == SEMA_OK) rc_ = growbuf_reserve(s->gValid, device, capacity_rows, 0);
+        if (rc_ != SEMA_OK) { sema_index_destroy(s); return rc_; }
+        s->X = reinterpret_cast<float *>(s->gX.base);
+        s->valid = reinterpret_cast<uint8_t *>(s->gValid.base);
+    } else {
+        CKD(cudaMalloc(&s->X, xbytes));
+        CKD(cudaMalloc(&s->valid, capacity_rows ? capacity_rows : 1));
+    }
     CKD(cudaMalloc(&s->q_dev, s->ld * sizeof(float)));
     CKD(cudaMemset(s->q_dev, 0, s->ld * sizeof(float)));
     CKD(cudaHostAlloc(&s->q_pin, s->ld * sizeof(float), cudaHostAllocPortable));
@@ -209,6 +239,10 @@ int sema_index_destroy(sema_index *s)
     if (s->own_stream) cudaStreamSynchronize(s->own_stream);
     if (s->ingest_stream) cudaStreamSynchronize(s->ingest_stream);
     for (auto &p : s->pending) cudaEventDestroy(p.ev);
+    if (s->growable) {
+        growbuf_free(s->gX); growbuf_free(s->gValid); growbuf_free(s->gPlanes);
+        s->X = nullptr; s->valid = nullptr; s->planes = nullptr;
+    }
     cudaFree(s->X); cudaFree(s->valid); cudaFree(s->q_dev); cudaFreeHost(s->q_pin);
     cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->keys_dev); cudaFree(s->res_dev);
     cudaFreeHost(s->res_pin); cudaFreeHost(s->res_map); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);

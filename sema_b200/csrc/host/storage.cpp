@@ -100,7 +100,12 @@ GpuVectorIndexer::~GpuVectorIndexer()
 Status GpuVectorIndexer::open(int device, uint32_t dim, uint64_t capacity_rows, bool normalize)
 {
     if (idx_) return Status::Err(SEMA_ERR_INVALID, "indexer already open");
-    int rc = sema_index_create(device, dim, capacity_rows, SEMA_METRIC_COSINE, &idx_);
+    // like the reference's table, the index grows as chunks arrive: capacity_rows bounds the address
+    // space only (0 = as many rows as 32-bit row ids allow); a driver without virtual memory
+    // management gets the fixed-capacity index instead
+    const uint64_t max_rows = capacity_rows ? capacity_rows : 0xfffffffeull;
+    int rc = sema_index_create_growable(device, dim, max_rows, SEMA_METRIC_COSINE, &idx_);
+    if (rc == SEMA_ERR_UNSUPPORTED && capacity_rows) rc = sema_index_create(device, dim, capacity_rows, SEMA_METRIC_COSINE, &idx_);
     if (rc) return from_rc(rc);
     dim_ = dim;
     normalize_ = normalize;

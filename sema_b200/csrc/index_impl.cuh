@@ -19,6 +19,7 @@
 
 #include "../../include/sema_b200.h"
 #include "common.cuh"
+#include "growbuf.cuh"
 
 namespace sema_impl {
 
@@ -57,6 +58,10 @@ struct sema_index {
     int num_sms = 0;
     float *X = nullptr;
     uint8_t *valid = nullptr;
+    // growable index (sema_index_create_growable): X, valid and the K3 planes are address-space
+    // reservations of the maximum size, backed by physical memory as rows arrive
+    bool growable = false;
+    sema_impl::GrowBuf gX, gValid, gPlanes;
     uint64_t n_rows = 0;     // appended (enqueued)
     uint64_t n_visible = 0;  // ingest completed on the device
     uint64_t last_snapshot = 0;

@@ -24,10 +24,14 @@ class GpuIndex:
     ``LanceIndexer`` (``src/storage/lance_indexer.rs:19-28, 92-101``).
     """
 
-    def __init__(self, dim: int, capacity_rows: int, device: int = 0, metric: int = METRIC_COSINE):
+    def __init__(self, dim: int, capacity_rows: int, device: int = 0, metric: int = METRIC_COSINE,
+                 growable: bool = False):
+        """growable=True: ``capacity_rows`` only reserves address space; HBM is mapped as rows arrive
+        (``sema_index_create_growable``), like the reference's table, which grows without a declared size."""
         self._L = _lib.lib()
         self._h = C.c_void_p()
-        check(self._L.sema_index_create(device, dim, capacity_rows, metric, C.byref(self._h)))
+        create = self._L.sema_index_create_growable if growable else self._L.sema_index_create
+        check(create(device, dim, capacity_rows, metric, C.byref(self._h)))
         self.dim = dim
         self.metric = metric
         self.device = device

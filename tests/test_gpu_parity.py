@@ -956,3 +956,57 @@ def test_query_stream_interleaved_with_appends_and_host_searches(sema, oracle_c)
                 h_ids, h_sc = idx.search(Q[i], k)
                 assert np.array_equal(h_ids, ids[i, :nf[i]]) and np.array_equal(h_sc, sc[i, :nf[i]])
             assert idx.last_snapshot == hi
+
+
+# ---------------------------------------------------------------- growable index (virtual-memory backed)
+def test_growable_index_grows_in_place_and_matches_oracle(sema, oracle_c):
+    """sema_index_create_growable: max_rows reserves address space only; appends map HBM in 256 MB steps
+    (174 762 rows of dim 384 each), the matrix stays contiguous and every search sees exactly the oracle's rows."""
+    import torch
+    d, k = 384, 10
+    free0, _ = torch.cuda.mem_get_info(0)
+    with sema.GpuIndex(d, 60_000_000, growable=True) as idx:          # 92 GB of address space, nothing committed
+        assert idx.capacity == 60_000_000 and len(idx) == 0
+        free1, _ = torch.cuda.mem_get_info(0)
+        assert free0 - free1 < (1 << 30)                                # creating it costs (almost) no HBM
+        ids, sc = idx.search(_unit(2, 1, d)[0], k)
+        assert len(ids) == 0
+        total = 0
+        Q = _unit(2, 3, d)
+        for n_add in (1000, 173_000, 2_000, 190_000):                   # the 2nd and 4th appends cross a 256 MB step
+            idx.append_synthetic(seed=1, row0=total, n=n_add, normalize=True)
+            total += n_add
+            X = oracle_c.normalize(oracle_c.synth(1, 0, total, d))
+            for q in Q:
+                ids, sc = idx.search(q, k)
+                r_ids, r_sc = oracle_c.scan(X, q, k)
+                O.check_parity(ids, sc, r_ids, r_sc)
+        free2, _ = torch.cuda.mem_get_info(0)
+        assert free1 - free2 < 3 * (256 << 20) + (64 << 20)             # 366 k rows = 562 MB -> three steps
+        # the batched tensor-core path builds its planes in a growable buffer too
+        Qb = _unit(3, 9, d)
+        idx.set_batch_mode(2)
+        b_ids, b_sc, b_nf = idx.search_batch(Qb, k)
+        assert idx.batch_stats()[0] == 9
+        for i in range(9):
+            r_ids, r_sc = oracle_c.scan(X, Qb[i], k)
+            O.check_parity(b_ids[i, :b_nf[i]], b_sc[i, :b_nf[i]], r_ids, r_sc)
+        # deletions and compaction work on the mapped prefix
+        idx.tombstone(np.arange(0, 1000, dtype=np.uint64))
+        idx.compact()
+        assert len(idx) == total - 1000
+        ids, sc = idx.search(Q[0], k)
+        valid = np.ones(total, np.uint8)
+        valid[:1000] = 0
+        r_ids, r_sc = oracle_c.scan(X, Q[0], k, 0, valid)
+        O.check_parity(ids + 1000, sc, r_ids, r_sc)                     # rows moved down by the 1000 dropped
+
+
+def test_growable_index_respects_max_rows(sema):
+    with sema.GpuIndex(384, 100, growable=True) as idx:
+        idx.append(_unit(1, 100, 384), normalize=False)
+        with pytest.raises(sema.SemaError) as e:
+            idx.append(_unit(1, 1, 384), normalize=False)
+        assert e.value.code == -3                                        # SEMA_ERR_CAPACITY
+        ids, _ = idx.search(_unit(1, 100, 384)[5], 3)
+        assert ids[0] == 5
