@@ -194,6 +194,16 @@ int sema_topk_merge_device(sema_index *idx, const uint64_t *keys_dev, uint32_t n
                            uint32_t k, uint64_t *ids_dev, float *scores_dev,
                            uint32_t *n_found_dev);
 
+/* Batched forms of the two calls above, for the corpus-sharded batched search (SURVEY.md §8(e):
+ * every shard runs the batch on its rows — K3 when the shape allows — and contributes nq x k packed
+ * keys to one all-gather; kernel K4 then merges per query).  keys_dev of the first: [nq][k];
+ * keys_dev of the second: [n_lists][nq][k] (the all-gathered buffer), k <= 128. */
+int sema_index_search_batch_keys_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
+                                        uint64_t *keys_dev);
+int sema_topk_merge_batch_device(sema_index *idx, const uint64_t *keys_dev, uint32_t n_lists,
+                                 uint32_t nq, uint32_t k, uint64_t *ids_dev, float *scores_dev,
+                                 uint32_t *n_found_dev);
+
 /* ---- corpus-sharded group: scan + exchange + merge in ONE kernel per rank -------------
  * One process per GPU; every rank holds a contiguous row range (sema_index_set_row_base).  The
  * last block of K2 stores the shard's top-k keys straight into every rank's exchange buffer over

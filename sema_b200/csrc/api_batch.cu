@@ -1,6 +1,7 @@
 // api_batch.cu — K3: bf16 planes, cluster launch, exact re-scoring, K2 fallback; batched entry points.
 #include "index_impl.cuh"
 #include "k3_batch.cuh"
+#include "k4_merge.cuh"
 
 using namespace sema;
 using namespace sema_impl;
@@ -356,7 +357,81 @@ int scan_stream(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_
 
 }  // namespace sema_impl
 
+namespace {
+
+// the handle's own device buffers for a batch result: ids / scores [nq][k], n_found [nq]
+int ensure_batch_results(sema_index *s, uint32_t nq, uint32_t k)
+{
+    if (s->batch_cap_res < (size_t)nq * k) {
+        cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
+        s->bids_dev = nullptr; s->bsc_dev = nullptr; s->batch_cap_res = 0;
+        CK(cudaMalloc(&s->bids_dev, (size_t)nq * k * sizeof(uint64_t)));
+        CK(cudaMalloc(&s->bsc_dev, (size_t)nq * k * sizeof(float)));
+        s->batch_cap_res = (size_t)nq * k;
+    }
+    if (s->batch_cap_nf < nq) {
+        cudaFree(s->bnf_dev);
+        s->bnf_dev = nullptr; s->batch_cap_nf = 0;
+        CK(cudaMalloc(&s->bnf_dev, (size_t)nq * sizeof(uint32_t)));
+        s->batch_cap_nf = nq;
+    }
+    return SEMA_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
+int sema_index_search_batch_keys_device(sema_index *s, const float *Q_dev, uint32_t nq, uint32_t k, uint64_t *keys_dev)
+{
+    if (!s || !Q_dev || !keys_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || k > SEMA_MAX_K || nq == 0) return fail(SEMA_ERR_INVALID, "k %u / nq %u out of range", k, nq);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    if (n == 0) {
+        CK(cudaMemsetAsync(keys_dev, 0, (size_t)nq * k * sizeof(uint64_t), s->stream));
+        return SEMA_OK;
+    }
+    rc = ensure_batch_results(s, nq, k);
+    if (rc) return rc;
+    rc = batch_core(s, Q_dev, nq, (uint32_t)n, k, s->bids_dev, s->bsc_dev, s->bnf_dev);
+    if (rc) return rc;
+    const size_t total = (size_t)nq * k;
+    const unsigned blocks = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    if (s->metric == SEMA_METRIC_L2)
+        pack_keys_kernel<METRIC_L2><<<blocks, 256, 0, s->stream>>>(s->bids_dev, s->bsc_dev, s->bnf_dev, nq, k, keys_dev);
+    else
+        pack_keys_kernel<METRIC_COSINE><<<blocks, 256, 0, s->stream>>>(s->bids_dev, s->bsc_dev, s->bnf_dev, nq, k, keys_dev);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
+int sema_topk_merge_batch_device(sema_index *s, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k,
+                                 uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
+{
+    if (!s || !keys_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k == 0 || nq == 0 || n_lists == 0) return fail(SEMA_ERR_INVALID, "k %u / nq %u / n_lists %u out of range", k, nq, n_lists);
+    if (k > (uint32_t)K_PASS) return fail(SEMA_ERR_UNSUPPORTED, "the batched merge covers k <= %d", K_PASS);
+    if ((uint64_t)n_lists * k > 0x7fffffffull) return fail(SEMA_ERR_INVALID, "too many candidates");
+    CK(cudaSetDevice(s->device));
+    const bool l2 = s->metric == SEMA_METRIC_L2;
+#define SEMA_MERGE_BATCH(M)                                                                                             \
+    do {                                                                                                                \
+        if (l2) merge_topk_batch_kernel<M, METRIC_L2><<<nq, MERGE_THREADS, 0, s->stream>>>(keys_dev, n_lists, nq, (int)k, ids_dev, scores_dev, n_found_dev); \
+        else merge_topk_batch_kernel<M, METRIC_COSINE><<<nq, MERGE_THREADS, 0, s->stream>>>(keys_dev, n_lists, nq, (int)k, ids_dev, scores_dev, n_found_dev); \
+    } while (0)
+    if (k <= 32) SEMA_MERGE_BATCH(1);
+    else if (k <= 64) SEMA_MERGE_BATCH(2);
+    else SEMA_MERGE_BATCH(4);
+#undef SEMA_MERGE_BATCH
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
 
 int sema_index_search_batch(sema_index *s, const float *Q, uint32_t nq, uint32_t k,
                             uint64_t *row_ids, float *scores, uint32_t *n_found)
@@ -374,14 +449,8 @@ int sema_index_search_batch(sema_index *s, const float *Q, uint32_t nq, uint32_t
     if (k == 0 || n == 0 || nq == 0) return SEMA_OK;
     rc = ensure(reinterpret_cast<void **>(&s->Q_dev), &s->batch_cap_q, (size_t)nq * s->dim * sizeof(float));
     if (rc) return rc;
-    if (s->batch_cap_res < (size_t)nq * k) {
-        cudaFree(s->bids_dev); cudaFree(s->bsc_dev); cudaFree(s->bnf_dev);
-        s->bids_dev = nullptr; s->bsc_dev = nullptr; s->bnf_dev = nullptr; s->batch_cap_res = 0;
-        CK(cudaMalloc(&s->bids_dev, (size_t)nq * k * sizeof(uint64_t)));
-        CK(cudaMalloc(&s->bsc_dev, (size_t)nq * k * sizeof(float)));
-        CK(cudaMalloc(&s->bnf_dev, (size_t)nq * sizeof(uint32_t)));
-        s->batch_cap_res = (size_t)nq * k;
-    }
+    rc = ensure_batch_results(s, nq, k);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(s->Q_dev, Q, (size_t)nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     if (s->normalize_queries) {
         rc = normalize_queries_dev(s, s->Q_dev, s->dim, nq);

@@ -86,7 +86,7 @@ struct sema_index {
     uint64_t *bids_dev = nullptr;
     float *bsc_dev = nullptr;
     uint32_t *bnf_dev = nullptr;
-    size_t batch_cap_q = 0, batch_cap_res = 0;
+    size_t batch_cap_q = 0, batch_cap_res = 0, batch_cap_nf = 0;
     uint64_t *tomb_dev = nullptr;
     size_t tomb_cap = 0;
     std::deque<sema_impl::Pending> pending;

@@ -230,6 +230,15 @@ class GpuIndex:
                                              C.c_void_p(ids_ptr), C.c_void_p(scores_ptr),
                                              C.c_void_p(nfound_ptr)))
 
+    def search_batch_keys_device(self, q_ptr: int, nq: int, k: int, keys_ptr: int) -> None:
+        check(self._L.sema_index_search_batch_keys_device(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(keys_ptr)))
+
+    def merge_batch_device(self, keys_ptr: int, n_lists: int, nq: int, k: int, ids_ptr: int, scores_ptr: int,
+                           nfound_ptr: int) -> None:
+        check(self._L.sema_topk_merge_batch_device(self._h, C.c_void_p(keys_ptr), n_lists, nq, k,
+                                                   C.c_void_p(ids_ptr), C.c_void_p(scores_ptr),
+                                                   C.c_void_p(nfound_ptr)))
+
     # -- properties -------------------------------------------------------------------
     def set_row_base(self, base: int) -> None:
         check(self._L.sema_index_set_row_base(self._h, base))

@@ -75,3 +75,27 @@ class ShardedSearcher:
         self.stream.synchronize()
         nf = int(self.nf_h[0])
         return self.ids_h.numpy()[:nf].astype(np.uint64), self.sc_h.numpy()[:nf].copy()
+
+    def search_batch(self, Q: np.ndarray):
+        """Batched sharded search: every rank calls this with the same nq queries; each runs the batch
+        on its shard (K3 on the tensor cores when the shape allows), one all-gather moves the
+        nq x k packed keys of every shard, and the batched K4 merges per query.
+        -> (ids uint64 [nq, k], scores float32 [nq, k], n_found int32 [nq]) on every rank."""
+        t = self.torch
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        nq, k = Q.shape[0], self.k
+        Qd = t.from_numpy(Q).to(self.dev, non_blocking=False)
+        keys_local = t.zeros(nq * k, dtype=t.int64, device=self.dev)
+        ids_d = t.zeros((nq, k), dtype=t.int64, device=self.dev)
+        sc_d = t.zeros((nq, k), dtype=t.float32, device=self.dev)
+        nf_d = t.zeros(nq, dtype=t.int32, device=self.dev)
+        self.idx.search_batch_keys_device(Qd.data_ptr(), nq, k, keys_local.data_ptr())
+        if self.world > 1:
+            keys_all = t.zeros(self.world * nq * k, dtype=t.int64, device=self.dev)
+            self.dist.all_gather_into_tensor(keys_all, keys_local)       # [world][nq][k]
+        else:
+            keys_all = keys_local
+        self.idx.merge_batch_device(keys_all.data_ptr(), self.world, nq, k, ids_d.data_ptr(), sc_d.data_ptr(),
+                                    nf_d.data_ptr())
+        self.stream.synchronize()
+        return ids_d.cpu().numpy().astype(np.uint64), sc_d.cpu().numpy(), nf_d.cpu().numpy()

@@ -1010,3 +1010,63 @@ def test_growable_index_respects_max_rows(sema):
         assert e.value.code == -3                                        # SEMA_ERR_CAPACITY
         ids, _ = idx.search(_unit(1, 100, 384)[5], 3)
         assert ids[0] == 5
+
+
+# ---------------------------------------------------------------- sharded batched search (batched keys + batched K4)
+@pytest.mark.parametrize("G,k,nq,mode,metric", [(2, 10, 9, 0, 0), (4, 100, 5, 2, 0), (8, 10, 130, 3, 0), (3, 50, 6, 1, 1), (2, 128, 3, 1, 0)])
+def test_k4_batched_virtual_shards_equal_single_index(sema, oracle_c, G, k, nq, mode, metric):
+    # SURVEY.md §8(e), batched: every shard contributes nq x k packed keys (K3 or the K2 loop), the
+    # all-gather is a concatenation here, the batched K4 merges per query
+    import torch
+    n, d = 24000, 384
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    valid = np.ones(n, np.uint8)
+    valid[::9] = 0
+    per = n // G
+    dev = torch.device("cuda:0")
+    Q_dev = torch.from_numpy(Q).to(dev)
+    keys = torch.zeros(G * nq * k, dtype=torch.int64, device=dev)
+    ids_d = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+    sc_d = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+    nf_d = torch.zeros(nq, dtype=torch.int32, device=dev)
+    shards = []
+    try:
+        for g in range(G):
+            lo, hi = g * per, (n if g == G - 1 else (g + 1) * per)
+            s = sema.GpuIndex(d, hi - lo, metric=metric)
+            s.set_row_base(lo)
+            s.append(X[lo:hi], valid=valid[lo:hi], normalize=False)
+            s.set_batch_mode(mode)
+            s.set_stream(torch.cuda.current_stream().cuda_stream)
+            shards.append(s)
+        for g, s in enumerate(shards):
+            s.search_batch_keys_device(Q_dev.data_ptr(), nq, k, keys.data_ptr() + g * nq * k * 8)
+        shards[0].merge_batch_device(keys.data_ptr(), G, nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        for s in shards:
+            s.close()
+    ids, sc, nf = ids_d.cpu().numpy().astype(np.uint64), sc_d.cpu().numpy(), nf_d.cpu().numpy()
+    for i in range(nq):
+        r_ids, r_sc = oracle_c.scan(X, Q[i], k, metric, valid)
+        assert nf[i] == len(r_ids)
+        O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+
+
+def test_sharded_searcher_batch_world1(sema, oracle_c):
+    # sema_b200.sharded.ShardedSearcher.search_batch with a single rank (no process group): the same
+    # code path bench.py --workload batch --gpus N drives under torchrun
+    from sema_b200.sharded import ShardedSearcher
+    n, d, k, nq = 30000, 384, 10, 20
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.set_row_base(500)
+        idx.append(X, normalize=False)
+        sh = ShardedSearcher(idx, None, k)
+        ids, sc, nf = sh.search_batch(Q)
+        idx.set_stream(None)
+    for i in range(nq):
+        r_ids, r_sc = oracle_c.scan(X, Q[i], k, id_base=500)
+        O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)

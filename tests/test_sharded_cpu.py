@@ -88,3 +88,46 @@ def test_two_rank_allgather_merge_equals_global_scan(n, k, metric):
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def _worker_batch(rank, world, port, n, d, k, nq, out):
+    """Batched sharded search, host logic: every rank contributes [nq][k] keys, one all-gather yields
+    [world][nq][k], the merge runs per query (kernel K4's batched form does this on the device)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        X = O.normalize(O.synth(1, 0, n, d))
+        Q = O.normalize(O.synth(2, 0, nq, d))
+        lo, hi = shard_range(n, world, rank)
+        mine = np.zeros((nq, k), dtype=np.uint64)
+        for i in range(nq):
+            ids, sc = O.scan(X[lo:hi], Q[i], k, 0, id_base=lo)
+            mine[i, :len(ids)] = K.pack_keys(sc, ids, 0)
+        gathered = torch.zeros(world * nq * k, dtype=torch.int64)
+        dist.all_gather_into_tensor(gathered, torch.from_numpy(mine.view(np.int64).ravel()))
+        allk = gathered.numpy().view(np.uint64).reshape(world, nq, k)
+        for i in range(nq):
+            g_ids, g_sc = K.unpack_keys(K.merge_keys([allk[:, i, :]], k), 0)
+            r_ids, r_sc = O.scan(X, Q[i], k, 0)
+            assert np.array_equal(g_ids, r_ids) and np.array_equal(g_sc, r_sc), (rank, i)
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_batched_allgather_merge_equals_global_scan():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_batch, args=(r, 2, port, 3001, 64, 10, 5, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
