@@ -675,6 +675,8 @@ def run_ours(a):
         idx.set_scan_variant(600)
 
     def run_device(nq):
+        if nq <= 0:
+            return
         if use_stream:
             (idx if world == 1 else group).search_stream_device(Qs.data_ptr(), nq, k, ids_s.data_ptr(), sc_s.data_ptr(),
                                                                nf_s.data_ptr())
