@@ -186,12 +186,65 @@ __device__ __forceinline__ void block_merge_n(WarpTopK<M> &top, uint64_t *sm, in
     }
 }
 
+// ---- selection by rounds, for small k ------------------------------------------------------
+// The merges after the scan sit on the latency path of every search (they are what is left of a
+// query on a small corpus).  Inserting candidates one at a time into the sorted warp list costs a
+// ~200-cycle shuffle chain per insertion, and merging P lists of k needs ~k(1 + ln P) of them.  For
+// k <= SELECT_MAX_K it is cheaper to hold the candidates unsorted, C per lane, and extract the
+// maximum k times: one round = C compares + a 5-step butterfly.  Keys are unique (the row id is
+// part of the key), so clearing "the key equal to the maximum" removes exactly one candidate.
+constexpr int SELECT_MAX_K = 16;
+constexpr int SELECT_C = 10;     // candidates per lane the last-block merge can hold (148 blocks x k = 16 -> 2368 keys over 8 warps)
+
+template <int M, int C>
+__device__ __forceinline__ void warp_select(WarpTopK<M> &top, uint64_t (&c)[C], int k, int lane)
+{
+    uint64_t mine = 0;           // lane r ends up with the r-th best
+    for (int r = 0; r < k; ++r) {
+        uint64_t m = c[0];
+#pragma unroll
+        for (int i = 1; i < C; ++i) m = c[i] > m ? c[i] : m;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const uint64_t o = __shfl_xor_sync(FULL, m, d);
+            m = o > m ? o : m;
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+            if (c[i] == m) c[i] = 0;
+        if (lane == r) mine = m;
+    }
+    top.init();
+    top.v[0] = mine;
+    top.thr = __shfl_sync(FULL, mine, k - 1);
+}
+
+// per-warp lists (first k entries each) -> warp 0's list, by selection; NACTIVE <= 8, k <= 16
+template <int M, int NACTIVE>
+__device__ __forceinline__ void block_select(WarpTopK<M> &top, uint64_t *sm, int warp, int lane, int k)
+{
+    static_assert(NACTIVE * SELECT_MAX_K <= 4 * 32, "four candidates per lane");
+    if (warp < NACTIVE) top.store(sm + warp * 32 * M, lane);
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = i * 32 + lane, w = f / k, e = f - w * k;
+            c[i] = f < NACTIVE * k ? sm[w * 32 * M + e] : 0ull;
+        }
+        warp_select<M, 4>(top, c, k, lane);
+    }
+}
+
 template <int M, int METRIC, int NW, int NACTIVE>
 __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &p, uint64_t *sm_keys, bool *is_last,
                                             int warp, int lane)
 {
     const int k = (int)p.k;
-    block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
+    const bool by_rounds = M == 1 && k <= SELECT_MAX_K;     // small k: selection by rounds (see warp_select)
+    if (by_rounds) block_select<M, NACTIVE>(top, sm_keys, warp, lane, k);
+    else block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
     if (warp == 0) top.store(p.partials + (size_t)blockIdx.x * 32 * M, lane);
     __threadfence();
     __syncthreads();
@@ -201,13 +254,25 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
     __threadfence();
 
     // Only the first k entries of each block list matter.  They are read as one flat array of
-    // gridDim.x * k keys, U independent loads per lane in flight: this merge sits on the critical
-    // path after the last block arrives, so its load latency must overlap, not add up.
-    top.init();
+    // gridDim.x * k keys with all of a lane's loads in flight at once: this merge sits on the
+    // critical path after the last block arrives, so its load latency must overlap, not add up.
     const int chunks = (k + 31) >> 5;
-    {
+    const int totalk = (int)gridDim.x * k;
+    if (by_rounds && totalk <= NACTIVE * 32 * SELECT_C) {
+        if (warp < NACTIVE) {
+            uint64_t c[SELECT_C];
+#pragma unroll
+            for (int i = 0; i < SELECT_C; ++i) {
+                const int idx = (i * NACTIVE + warp) * 32 + lane;
+                const int bb = idx / k, e = idx - bb * k;
+                c[i] = idx < totalk ? __ldcg(p.partials + (size_t)bb * 32 * M + e) : 0ull;
+            }
+            warp_select<M, SELECT_C>(top, c, k, lane);
+        }
+        block_select<M, NACTIVE>(top, sm_keys, warp, lane, k);
+    } else {
+        top.init();
         constexpr int U = 8;
-        const int totalk = (int)gridDim.x * k;
         for (int base = warp * 32; warp < NACTIVE && base < totalk; base += NACTIVE * 32 * U) {
             uint64_t kk[U];
 #pragma unroll
@@ -219,8 +284,8 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
 #pragma unroll
             for (int u = 0; u < U; ++u) top.offer(kk[u], kk[u] != 0, lane, k);
         }
+        block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
     }
-    block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
 
     bool timed_out = false;
     if (p.x.world >= 1) {
@@ -250,14 +315,28 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
         }
         __syncthreads();
         timed_out = !*is_last;
-        top.init();
-        const int total_x = (int)world * chunks;
-        for (int i = warp; warp < NACTIVE && i < total_x; i += NACTIVE) {
-            const int g = i / chunks, j = i - g * chunks;
-            const uint64_t key = __ldcv(xchg_keys(mine, world, slot, (uint32_t)g) + j * 32 + lane);
-            top.offer(key, key != 0, lane, k);
+        if (by_rounds) {
+            // world * k <= 16 * 16 keys: warp 0 selects alone, 8 candidates per lane
+            static_assert(XCHG_MAX_WORLD * SELECT_MAX_K <= 8 * 32, "eight candidates per lane");
+            if (warp == 0) {
+                uint64_t c[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int f = i * 32 + lane, g = f / k, e = f - g * k;
+                    c[i] = f < (int)world * k ? __ldcv(xchg_keys(mine, world, slot, (uint32_t)g) + e) : 0ull;
+                }
+                warp_select<M, 8>(top, c, k, lane);
+            }
+        } else {
+            top.init();
+            const int total_x = (int)world * chunks;
+            for (int i = warp; warp < NACTIVE && i < total_x; i += NACTIVE) {
+                const int g = i / chunks, j = i - g * chunks;
+                const uint64_t key = __ldcv(xchg_keys(mine, world, slot, (uint32_t)g) + j * 32 + lane);
+                top.offer(key, key != 0, lane, k);
+            }
+            block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
         }
-        block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
     }
     if (warp == 0) {
         emit_results<M, METRIC>(top, k, p.out_keys, p.res_ids, p.res_scores, p.res_nfound, lane);
