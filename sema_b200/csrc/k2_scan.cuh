@@ -165,27 +165,6 @@ __device__ __forceinline__ void emit_results(const WarpTopK<M> &top, int k, uint
     if (res_nfound && lane == 0) *res_nfound = (uint32_t)found;
 }
 
-// Everything after a block's warps have scanned their rows, shared by the LDG and the TMA variant:
-// per-warp lists -> block list -> global partials; the last block to arrive (atomic ticket) merges
-// all block lists, optionally exchanges with the other shards (Exchange), and emits the result.
-// NW = warps in the block, NACTIVE = warps (0..NACTIVE-1) that hold lists / take part in the merges.
-template <int M>
-__device__ __forceinline__ void block_merge_n(WarpTopK<M> &top, uint64_t *sm, int warp, int lane, int k, int nw,
-                                              int nactive)
-{
-    (void)nw;
-    if (warp < nactive) top.store(sm + warp * 32 * M, lane);
-    __syncthreads();
-    if (warp == 0) {
-        const int chunks = (k + 31) >> 5;  // entries past k never matter
-        for (int w = 1; w < nactive; ++w)
-            for (int j = 0; j < chunks; ++j) {
-                const uint64_t key = sm[w * 32 * M + j * 32 + lane];
-                top.offer(key, key != 0, lane, k);
-            }
-    }
-}
-
 // ---- selection by rounds, for small k ------------------------------------------------------
 // The merges after the scan sit on the latency path of every search (they are what is left of a
 // query on a small corpus).  Inserting candidates one at a time into the sorted warp list costs a
@@ -237,6 +216,72 @@ __device__ __forceinline__ void block_select(WarpTopK<M> &top, uint64_t *sm, int
     }
 }
 
+// ---- merging sorted lists, for larger k -----------------------------------------------------
+// Every list in flight after the scan is sorted (descending over e = j*32 + lane, 32*M entries, zeros
+// last).  Two such lists merge without any insertion: C[e] = max(A[e], B[32M-1-e]) holds the 32M
+// largest keys of the union as a bitonic sequence (the half-cleaner property), which log2(32M)
+// compare-exchange stages sort — the first log2(M) between registers, the last five by shuffle.
+// brev[j] must hold the other list reversed: other[(M-1-j)*32 + (31-lane)].
+template <int M>
+__device__ __forceinline__ void bitonic_merge_in(WarpTopK<M> &top, const uint64_t (&brev)[M], int lane)
+{
+#pragma unroll
+    for (int j = 0; j < M; ++j) top.v[j] = top.v[j] > brev[j] ? top.v[j] : brev[j];
+#pragma unroll
+    for (int jd = M / 2; jd >= 1; jd >>= 1)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            if ((j & jd) == 0) {
+                const uint64_t a = top.v[j], b = top.v[j | jd];
+                top.v[j] = a > b ? a : b;
+                top.v[j | jd] = a > b ? b : a;
+            }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const bool upper = (lane & d) != 0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            const uint64_t o = __shfl_xor_sync(FULL, top.v[j], d);
+            const uint64_t hi = top.v[j] > o ? top.v[j] : o, lo = top.v[j] > o ? o : top.v[j];
+            top.v[j] = upper ? lo : hi;
+        }
+    }
+}
+
+template <int M>
+__device__ __forceinline__ void set_threshold(WarpTopK<M> &top, int k)
+{
+    const int kj = (k - 1) >> 5, kl = (k - 1) & 31;
+    uint64_t t = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+        if (j == kj) t = top.v[j];
+    top.thr = __shfl_sync(FULL, t, kl);
+}
+
+// per-warp sorted lists -> warp 0's list by bitonic merges
+template <int M, int NACTIVE>
+__device__ __forceinline__ void block_bitonic(WarpTopK<M> &top, uint64_t *sm, int warp, int lane, int k)
+{
+    if (warp < NACTIVE) top.store(sm + warp * 32 * M, lane);
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < NACTIVE; ++w) {
+            const uint64_t *l = sm + w * 32 * M;
+            if (l[0] == 0) continue;                       // empty list (warp-uniform)
+            uint64_t brev[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) brev[j] = l[(M - 1 - j) * 32 + (31 - lane)];
+            bitonic_merge_in<M>(top, brev, lane);
+        }
+        set_threshold<M>(top, k);
+    }
+}
+
+// Everything after a block's warps have scanned their rows, shared by the LDG and the TMA variant:
+// per-warp lists -> block list -> global partials; the last block to arrive (atomic ticket) merges
+// all block lists, optionally exchanges with the other shards (Exchange), and emits the result.
+// NW = warps in the block, NACTIVE = warps (0..NACTIVE-1) that hold lists / take part in the merges.
 template <int M, int METRIC, int NW, int NACTIVE>
 __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &p, uint64_t *sm_keys, bool *is_last,
                                             int warp, int lane)
@@ -244,7 +289,7 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
     const int k = (int)p.k;
     const bool by_rounds = M == 1 && k <= SELECT_MAX_K;     // small k: selection by rounds (see warp_select)
     if (by_rounds) block_select<M, NACTIVE>(top, sm_keys, warp, lane, k);
-    else block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
+    else block_bitonic<M, NACTIVE>(top, sm_keys, warp, lane, k);
     if (warp == 0) top.store(p.partials + (size_t)blockIdx.x * 32 * M, lane);
     __threadfence();
     __syncthreads();
@@ -256,7 +301,6 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
     // Only the first k entries of each block list matter.  They are read as one flat array of
     // gridDim.x * k keys with all of a lane's loads in flight at once: this merge sits on the
     // critical path after the last block arrives, so its load latency must overlap, not add up.
-    const int chunks = (k + 31) >> 5;
     const int totalk = (int)gridDim.x * k;
     if (by_rounds && totalk <= NACTIVE * 32 * SELECT_C) {
         if (warp < NACTIVE) {
@@ -271,20 +315,22 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
         }
         block_select<M, NACTIVE>(top, sm_keys, warp, lane, k);
     } else {
+        // whole block lists (32*M sorted keys each), U of them loaded ahead, merged without insertions
         top.init();
-        constexpr int U = 8;
-        for (int base = warp * 32; warp < NACTIVE && base < totalk; base += NACTIVE * 32 * U) {
-            uint64_t kk[U];
+        constexpr int U = M == 4 ? 2 : 4;
+        for (int b0 = warp; warp < NACTIVE && b0 < (int)gridDim.x; b0 += NACTIVE * U) {
+            uint64_t brev[U][M];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int idx = base + u * NACTIVE * 32 + lane;
-                const int bb = idx / k, e = idx - bb * k;
-                kk[u] = idx < totalk ? __ldcg(p.partials + (size_t)bb * 32 * M + e) : 0ull;
+                const int bb = b0 + u * NACTIVE;
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    brev[u][j] = bb < (int)gridDim.x ? __ldcg(p.partials + (size_t)bb * 32 * M + (M - 1 - j) * 32 + (31 - lane)) : 0ull;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) top.offer(kk[u], kk[u] != 0, lane, k);
+            for (int u = 0; u < U; ++u) bitonic_merge_in<M>(top, brev[u], lane);
         }
-        block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
+        block_bitonic<M, NACTIVE>(top, sm_keys, warp, lane, k);
     }
 
     bool timed_out = false;
@@ -328,14 +374,16 @@ __device__ __forceinline__ void finish_topk(WarpTopK<M> &top, const ScanParams &
                 warp_select<M, 8>(top, c, k, lane);
             }
         } else {
+            // every rank published a sorted list of 32*M keys (zeros past k): merge them like block lists
             top.init();
-            const int total_x = (int)world * chunks;
-            for (int i = warp; warp < NACTIVE && i < total_x; i += NACTIVE) {
-                const int g = i / chunks, j = i - g * chunks;
-                const uint64_t key = __ldcv(xchg_keys(mine, world, slot, (uint32_t)g) + j * 32 + lane);
-                top.offer(key, key != 0, lane, k);
+            for (int g = warp; warp < NACTIVE && g < (int)world; g += NACTIVE) {
+                const uint64_t *l = xchg_keys(mine, world, slot, (uint32_t)g);
+                uint64_t brev[M];
+#pragma unroll
+                for (int j = 0; j < M; ++j) brev[j] = __ldcv(l + (M - 1 - j) * 32 + (31 - lane));
+                bitonic_merge_in<M>(top, brev, lane);
             }
-            block_merge_n<M>(top, sm_keys, warp, lane, k, NW, NACTIVE);
+            block_bitonic<M, NACTIVE>(top, sm_keys, warp, lane, k);
         }
     }
     if (warp == 0) {
