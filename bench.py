@@ -405,6 +405,15 @@ def run_batch_sharded(a):
     dist.destroy_process_group()
 
 
+def pool_traffic(a, n, seq, d):
+    """DRAM bytes per K0 launch from the committed ncu capture, when it is this exact workload."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return tr.get(f"k0_pool_{n}x{seq}x{d}_full_masks") if a.pool_full_mask else None
+    except Exception:
+        return None
+
+
 def run_pool(a):
     """Kernel K0 (the step before the path): mean_pool of src/semantic/embeddings.rs:61-91 fused with the
     append, for batches of texts whose token embeddings are already on the device.  One step pools and
@@ -455,7 +464,7 @@ def run_pool(a):
                    "timing": "host wall clock around sema_index_append_pooled_device (synchronous: rows visible on return)",
                    "l2_flush": f"none needed: each step reads {read_bytes / 1e9:.2f} GB"},
         "roofline": {"bound": "hbm", "achieved": read_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": read_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": read_bytes,
+                     "frac": read_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": pool_traffic(a, n, seq, d), "algorithmic_bytes": read_bytes,
                      "kernel": "pool_kernel (K0)", "note": "algorithmic bytes = attended tokens x dim x 4 (padding rows are skipped)"},
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "verified": bool(np.array_equal(got, want)),
