@@ -781,6 +781,18 @@ def run_ours(a):
     qps = 1e3 / ms_step
     e2e_qps = a.steps / (e2e_ms / 1e3)
 
+    # ---- every result of the timed stream must equal the result of the same pool query earlier in
+    # the stream (query i = pool[i % pool]): any race between chained launches would break this
+    stream_consistent = None
+    if use_stream and a.steps > a.queries:
+        first = torch.arange(a.steps, device=dev) % a.queries
+        same = (ids_s[:a.steps] == ids_s[first]).all() & (sc_s[:a.steps] == sc_s[first]).all() & (nf_s[:a.steps] == nf_s[first]).all()
+        stream_consistent = bool(same.item())
+        if dist is not None:
+            c = torch.tensor([int(stream_consistent)], device=dev)
+            dist.all_reduce(c, op=dist.ReduceOp.MIN)
+            stream_consistent = bool(c.item())
+
     # ---- verification of the last device-side result against a fresh host-API search
     verified = None
     if not a.no_verify and world == 1:
@@ -868,7 +880,8 @@ def run_ours(a):
                           " the result block into mapped host memory (these bytes), the call polls its completion flag"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "verified": verified,
+        "verified": verified if stream_consistent is None else bool(verified and stream_consistent),
+        "stream_self_consistent": stream_consistent,
     }
     if world == 1 and not a.no_cpu_baseline:
         try:
