@@ -38,6 +38,7 @@ extern "C" {
 #define SEMA_METRIC_L2 1     /* score = sum (q-x)^2 = LanceDB `_distance`, best = smallest */
 
 #define SEMA_MAX_K 1024u   /* largest `limit`; k <= 128 is one fused pass, larger k = ceil(k/128) passes */
+#define SEMA_MAX_INFLIGHT 8 /* host searches submitted and not yet collected, per handle          */
 #define SEMA_MAX_DIM 8192u /* dim 384 / 768 have unrolled kernels; others use the generic kernel */
 
 typedef struct sema_index sema_index;
@@ -141,6 +142,18 @@ int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_i
  * flag into mapped host memory, which this call polls. */
 int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row_ids,
                       float *scores, uint32_t *n_found);
+/* Asynchronous form of sema_index_search for callers that keep several queries in flight (a search
+ * service rather than the reference's one-query-at-a-time TUI): submit returns as soon as the scan
+ * is enqueued (q is consumed before it returns) and hands out a ticket; collect waits for that
+ * ticket and fills the caller's buffers exactly like sema_index_search.  Up to SEMA_MAX_INFLIGHT
+ * tickets may be outstanding per handle; they complete in submission order and may be collected in
+ * any order.  Consecutive submitted scans are chained on the device (programmatic dependent launch),
+ * so with two or more in flight the handle serves host queries at the query-stream rate.  Shapes
+ * outside the fast path (dim other than 384 / 768, k > 128, normalised queries) run synchronously
+ * inside submit.  sema_index_search(q) == submit(q) + collect. */
+int sema_index_search_submit(sema_index *idx, const float *q, uint32_t k, uint64_t *ticket);
+int sema_index_search_collect(sema_index *idx, uint64_t ticket, uint64_t *row_ids, float *scores,
+                              uint32_t *n_found);
 /* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq].  With the
  * cosine metric, dim % 64 == 0, dim <= 768, k <= 100 and nq >= 4 this runs kernel K3 (tcgen05
  * tensor cores, bf16 split precision — see sema_index_set_batch_mode — with exact fp32
@@ -220,6 +233,11 @@ int sema_shard_group_local_handle(sema_shard_group *g, void *handle_out /* 64 by
 int sema_shard_group_connect(sema_shard_group *g, const void *handles /* world x 64 bytes, by rank */);
 int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uint64_t *row_ids,
                             float *scores, uint32_t *n_found);
+/* submit / collect forms of sema_shard_group_search (same contract as sema_index_search_submit;
+ * every rank submits the same queries in the same order) */
+int sema_shard_group_search_submit(sema_shard_group *g, const float *q, uint32_t k, uint64_t *ticket);
+int sema_shard_group_search_collect(sema_shard_group *g, uint64_t ticket, uint64_t *row_ids, float *scores,
+                                    uint32_t *n_found);
 int sema_shard_group_search_device(sema_shard_group *g, const float *q_dev, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
 /* nq group searches issued back to back (Q_dev: nq x dim, results nq x k); consecutive launches

@@ -49,6 +49,8 @@ SIGNATURES = {
     "sema_index_save": (C.c_int, [_vp, C.c_char_p]),
     "sema_index_load": (C.c_int, [C.c_char_p, C.c_int, C.c_uint64, C.POINTER(_vp)]),
     "sema_index_search": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _u32p]),
+    "sema_index_search_submit": (C.c_int, [_vp, _vp, C.c_uint32, _u64p]),
+    "sema_index_search_collect": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _u32p]),
     "sema_index_search_batch": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_index_search_batch_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_index_search_stream_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
@@ -64,6 +66,8 @@ SIGNATURES = {
     "sema_shard_group_local_handle": (C.c_int, [_vp, _vp]),
     "sema_shard_group_connect": (C.c_int, [_vp, _vp]),
     "sema_shard_group_search": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _u32p]),
+    "sema_shard_group_search_submit": (C.c_int, [_vp, _vp, C.c_uint32, _u64p]),
+    "sema_shard_group_search_collect": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _u32p]),
     "sema_shard_group_search_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
     "sema_shard_group_search_stream_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_shard_group_destroy": (C.c_int, [_vp]),

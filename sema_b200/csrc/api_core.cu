@@ -225,7 +225,6 @@ static int create_impl(int device, uint32_t dim, uint64_t capacity_rows, int met
     CKD(cudaHostAlloc(&s->res_map, RES_MAP_BYTES, cudaHostAllocPortable | cudaHostAllocMapped));
     memset(s->res_map, 0, RES_MAP_BYTES);
     CKD(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->res_map_dev), s->res_map, 0));
-    s->host_flag = reinterpret_cast<uint64_t *>(s->res_map_dev + RES_MAP_FLAG_OFF);
     CKD(cudaDeviceSynchronize());
 #undef CKD
     *out = s;

@@ -20,6 +20,7 @@ struct ScanArgs {
     uint32_t *res_nfound;
     const Exchange *x = nullptr;   // sharded mode: fused peer exchange (single pass only)
     unsigned flags = 0;            // SCAN_CHAINED, SCAN_HOST_QUERY (index_impl.cuh)
+    uint64_t host_ticket = 0;      // SCAN_HOST_QUERY: value stored to the slot's flag when the results are in place
 };
 
 void fill_params(sema_index *s, const ScanArgs &a, ScanParams &p)
@@ -94,8 +95,8 @@ int run_scan_tma(sema_index *s, const ScanArgs &a)
         static_assert(sizeof(ScanParams) + sizeof(qa) <= 4096, "kernel parameter space");
         memcpy(qa.v, a.q_dev, s->dim * sizeof(float));   // ld == dim for these shapes
         p.q = nullptr;
-        p.host_flag = s->host_flag;
-        p.host_seq = ++s->host_seq;
+        p.host_flag = reinterpret_cast<uint64_t *>(s->res_map_dev + (a.host_ticket % RES_SLOTS) * RES_SLOT_BYTES + RES_MAP_FLAG_OFF);
+        p.host_seq = a.host_ticket;
     } else {
         qa.unused = 0;
     }
@@ -199,10 +200,11 @@ int decode(sema_index *s, const uint64_t *keys, uint32_t k, uint64_t *ids, float
 namespace sema_impl {
 
 int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys,
-               uint64_t *res_ids, float *res_scores, uint32_t *res_nfound, const Exchange *x, unsigned flags)
+               uint64_t *res_ids, float *res_scores, uint32_t *res_nfound, const Exchange *x, unsigned flags,
+               uint64_t host_ticket)
 {
     if (k <= K_PASS) {
-        ScanArgs a{q_dev, n, k, nullptr, out_keys ? out_keys : s->keys_dev, res_ids, res_scores, res_nfound, x, flags};
+        ScanArgs a{q_dev, n, k, nullptr, out_keys ? out_keys : s->keys_dev, res_ids, res_scores, res_nfound, x, flags, host_ticket};
         return scan_pass(s, a);
     }
     if (flags & SCAN_HOST_QUERY) return fail(SEMA_ERR_UNSUPPORTED, "the host-query path covers k <= %d", K_PASS);
@@ -225,24 +227,31 @@ bool host_query_ok(const sema_index *s, uint32_t k)
            s->ld == s->dim && (ld4 == 96 || ld4 == 192) && s->res_map != nullptr;
 }
 
-int host_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const Exchange *x, uint64_t *row_ids,
-                   float *scores, uint32_t *n_found)
+// A host-query launch reads nothing but its parameters and rows [0, n) of X, and everything on this
+// stream that writes those rows synchronises before it returns (tombstones, compaction), so the
+// launch may always overlap the tail of whatever kernel precedes it: it is chained (PDL) whenever
+// chaining is enabled.  Its own merge / exchange / result phase still waits for the predecessor.
+int host_query_launch(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const Exchange *x, uint64_t ticket)
 {
-    uint64_t *ids_m = reinterpret_cast<uint64_t *>(s->res_map_dev + 8);
-    float *sc_m = reinterpret_cast<float *>(s->res_map_dev + 8 + 8 * (size_t)k);
-    int rc = scan_query(s, q_host, n, k, nullptr, ids_m, sc_m, reinterpret_cast<uint32_t *>(s->res_map_dev), x,
-                        SCAN_HOST_QUERY);
-    if (rc) return rc;
+    unsigned char *slot = s->res_map_dev + (ticket % RES_SLOTS) * RES_SLOT_BYTES;
+    uint64_t *ids_m = reinterpret_cast<uint64_t *>(slot + 8);
+    float *sc_m = reinterpret_cast<float *>(slot + 8 + 8 * (size_t)k);
+    return scan_query(s, q_host, n, k, nullptr, ids_m, sc_m, reinterpret_cast<uint32_t *>(slot), x,
+                      SCAN_HOST_QUERY | (s->chain ? SCAN_CHAINED : 0u), ticket);
+}
+
+int host_query_wait(sema_index *s, uint64_t ticket, uint32_t k, uint64_t *row_ids, float *scores, uint32_t *n_found)
+{
     // Poll the flag the last block stores after the results.  The stream is queried now and then so
     // that a failed launch / faulting kernel surfaces as an error instead of an endless wait.
-    const uint64_t want = s->host_seq;
-    volatile const uint64_t *flag = reinterpret_cast<volatile const uint64_t *>(s->res_map + RES_MAP_FLAG_OFF);
+    const unsigned char *slot = s->res_map + (ticket % RES_SLOTS) * RES_SLOT_BYTES;
+    volatile const uint64_t *flag = reinterpret_cast<volatile const uint64_t *>(slot + RES_MAP_FLAG_OFF);
     for (uint32_t spin = 1;; ++spin) {
-        if (*flag == want) break;
+        if (*flag == ticket) break;
         if ((spin & 0x3fffu) == 0) {
             const cudaError_t e = cudaStreamQuery(s->stream);
             if (e == cudaSuccess) {
-                if (*flag == want) break;
+                if (*flag == ticket) break;
                 return fail(SEMA_ERR_CUDA, "scan finished without publishing its result");
             }
             if (e != cudaErrorNotReady)
@@ -253,12 +262,58 @@ int host_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, c
 #endif
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
-    const uint32_t nf = *reinterpret_cast<const uint32_t *>(s->res_map);
+    const uint32_t nf = *reinterpret_cast<const uint32_t *>(slot);
     if (nf == 0xffffffffu) return fail(SEMA_ERR_CUDA, "shard exchange timed out: a rank did not take part in the search");
     *n_found = nf;
-    memcpy(row_ids, s->res_map + 8, nf * sizeof(uint64_t));
-    memcpy(scores, s->res_map + 8 + 8 * (size_t)k, nf * sizeof(float));
+    memcpy(row_ids, slot + 8, nf * sizeof(uint64_t));
+    memcpy(scores, slot + 8 + 8 * (size_t)k, nf * sizeof(float));
     return SEMA_OK;
+}
+
+int slot_claim(sema_index *s, uint32_t k, uint64_t *ticket)
+{
+    const uint64_t t = s->host_seq + 1;
+    sema_index::Slot &sl = s->slots[t % RES_SLOTS];
+    if (sl.ticket != 0)
+        return fail(SEMA_ERR_INVALID, "%d searches are already in flight on this handle: collect ticket %llu first",
+                    RES_SLOTS, (unsigned long long)sl.ticket);
+    s->host_seq = t;
+    sl.ticket = t;
+    sl.k = k;
+    sl.sync_done = false;
+    sl.nf = 0;
+    *ticket = t;
+    return SEMA_OK;
+}
+
+int slot_collect(sema_index *s, uint64_t ticket, uint64_t *row_ids, float *scores, uint32_t *n_found)
+{
+    sema_index::Slot &sl = s->slots[ticket % RES_SLOTS];
+    if (ticket == 0 || sl.ticket != ticket) return fail(SEMA_ERR_INVALID, "ticket %llu is not outstanding", (unsigned long long)ticket);
+    int rc = SEMA_OK;
+    if (sl.sync_done) {
+        *n_found = sl.nf;
+        memcpy(row_ids, sl.ids.data(), sl.nf * sizeof(uint64_t));
+        memcpy(scores, sl.sc.data(), sl.nf * sizeof(float));
+    } else {
+        rc = host_query_wait(s, ticket, sl.k, row_ids, scores, n_found);
+    }
+    sl.ticket = 0;      // the slot is free again, whatever the outcome
+    return rc;
+}
+
+int host_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const Exchange *x, uint64_t *row_ids,
+                   float *scores, uint32_t *n_found)
+{
+    uint64_t ticket = 0;
+    int rc = slot_claim(s, k, &ticket);
+    if (rc) return rc;
+    rc = host_query_launch(s, q_host, n, k, x, ticket);
+    if (rc) {
+        s->slots[ticket % RES_SLOTS].ticket = 0;
+        return rc;
+    }
+    return slot_collect(s, ticket, row_ids, scores, n_found);
 }
 
 }  // namespace sema_impl
@@ -297,6 +352,40 @@ int sema_index_search(sema_index *s, const float *q, uint32_t k, uint64_t *row_i
     memcpy(row_ids, s->res_pin + 8, nf * sizeof(uint64_t));
     memcpy(scores, s->res_pin + 8 + 8 * (size_t)k, nf * sizeof(float));
     return SEMA_OK;
+}
+
+int sema_index_search_submit(sema_index *s, const float *q, uint32_t k, uint64_t *ticket)
+{
+    if (!s || !q || !ticket) return fail(SEMA_ERR_INVALID, "null argument");
+    if (k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u > SEMA_MAX_K %u", k, SEMA_MAX_K);
+    CK(cudaSetDevice(s->device));
+    int rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    rc = slot_claim(s, k, ticket);
+    if (rc) return rc;
+    sema_index::Slot &sl = s->slots[*ticket % RES_SLOTS];
+    if (k != 0 && n != 0 && host_query_ok(s, k)) {
+        s->last_snapshot = n;
+        rc = host_query_launch(s, q, (uint32_t)n, k, nullptr, *ticket);
+    } else {
+        // outside the fast path (or nothing to scan): answer now, hand the result out at collect
+        sl.ids.resize(k ? k : 1);
+        sl.sc.resize(k ? k : 1);
+        rc = sema_index_search(s, q, k, sl.ids.data(), sl.sc.data(), &sl.nf);
+        sl.sync_done = true;
+    }
+    if (rc) sl.ticket = 0;
+    return rc;
+}
+
+int sema_index_search_collect(sema_index *s, uint64_t ticket, uint64_t *row_ids, float *scores, uint32_t *n_found)
+{
+    if (!s || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
+    sema_index::Slot &sl = s->slots[ticket % RES_SLOTS];
+    if (ticket != 0 && sl.ticket == ticket && sl.k && (!row_ids || !scores)) return fail(SEMA_ERR_INVALID, "null output");
+    CK(cudaSetDevice(s->device));
+    return slot_collect(s, ticket, row_ids, scores, n_found);
 }
 
 int sema_index_search_keys_device(sema_index *s, const float *q_dev, uint32_t k, uint64_t *keys_dev)

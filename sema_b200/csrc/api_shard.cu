@@ -153,6 +153,45 @@ int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uin
     return SEMA_OK;
 }
 
+int sema_shard_group_search_submit(sema_shard_group *g, const float *q, uint32_t k, uint64_t *ticket)
+{
+    if (!g || !q || !ticket) return fail(SEMA_ERR_INVALID, "null argument");
+    int rc = group_check(g, k);
+    if (rc) return rc;
+    sema_index *s = g->idx;
+    CK(cudaSetDevice(s->device));
+    rc = poll_ingest(s, false);
+    if (rc) return rc;
+    const uint64_t n = s->n_visible;
+    s->last_snapshot = n;
+    rc = slot_claim(s, k, ticket);
+    if (rc) return rc;
+    sema_index::Slot &sl = s->slots[*ticket % RES_SLOTS];
+    if (host_query_ok(s, k)) {
+        Exchange x;
+        group_exchange(g, x);
+        x.seq = ++g->seq;
+        rc = host_query_launch(s, q, (uint32_t)n, k, &x, *ticket);
+    } else {
+        sl.ticket = 0;                                  // the synchronous call claims its own slot if it needs one
+        sl.ids.resize(k);
+        sl.sc.resize(k);
+        rc = sema_shard_group_search(g, q, k, sl.ids.data(), sl.sc.data(), &sl.nf);
+        sl.ticket = *ticket;
+        sl.sync_done = true;
+    }
+    if (rc) sl.ticket = 0;
+    return rc;
+}
+
+int sema_shard_group_search_collect(sema_shard_group *g, uint64_t ticket, uint64_t *row_ids, float *scores,
+                                    uint32_t *n_found)
+{
+    if (!g || !row_ids || !scores || !n_found) return fail(SEMA_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(g->idx->device));
+    return slot_collect(g->idx, ticket, row_ids, scores, n_found);
+}
+
 int sema_shard_group_destroy(sema_shard_group *g)
 {
     if (!g) return SEMA_OK;

@@ -45,7 +45,10 @@ constexpr int MAX_BLOCKS_PER_SM = 8;
 constexpr unsigned SCAN_CHAINED = 1u;      // directly follows another scan of the same call: may overlap it (PDL)
 constexpr unsigned SCAN_HOST_QUERY = 2u;   // q is a HOST pointer; query by kernel parameter, results + flag to res_map
 
-constexpr size_t RES_MAP_BYTES = 4096;     // mapped result block: [n_found u32, pad][ids u64 k][scores f32 k] ... [flag u64 @ 2048]
+// mapped result slots of the host-query path; one slot: [n_found u32, pad][ids u64 k][scores f32 k] ... [flag u64 @ 2048]
+constexpr int RES_SLOTS = SEMA_MAX_INFLIGHT;
+constexpr size_t RES_SLOT_BYTES = 4096;
+constexpr size_t RES_MAP_BYTES = RES_SLOTS * RES_SLOT_BYTES;
 constexpr size_t RES_MAP_FLAG_OFF = 2048;
 
 }  // namespace sema_impl
@@ -74,8 +77,15 @@ struct sema_index {
     uint64_t scan_seq = 0;            // TMA scans launched (selects the claim counter)
     unsigned char *res_map = nullptr; // mapped pinned host memory the host-query path writes results to (RES_MAP_BYTES)
     unsigned char *res_map_dev = nullptr;   // its device address
-    uint64_t *host_flag = nullptr;    // device address of the completion flag inside res_map
-    uint64_t host_seq = 0;            // value the next host-query launch will store there
+    uint64_t host_seq = 0;            // tickets issued so far; ticket t uses slot t % RES_SLOTS and stores t to its flag
+    struct Slot {                     // one submitted host search (sema_index_search_submit)
+        uint64_t ticket = 0;          // 0 = free
+        uint32_t k = 0;
+        bool sync_done = false;       // shape outside the fast path: the search ran synchronously at submit
+        uint32_t nf = 0;
+        std::vector<uint64_t> ids;
+        std::vector<float> sc;
+    } slots[sema_impl::RES_SLOTS];
     int chain = 1;                    // 0 = query streams never chain consecutive scans with PDL (tuning / comparison)
     int host_path = 1;                // 0 = host searches always stage through q_dev / res_dev (tuning / comparison)
     uint64_t *keys_dev = nullptr;     // SEMA_MAX_K keys (multi-pass scratch)
@@ -134,14 +144,22 @@ int launch_pool(sema_index *s, cudaStream_t stream, const float *tokens_dev, con
                 uint32_t seq_len, int skip_masked, float *out_dev, uint64_t out_ld);
 // api_search.cu: best k (any k <= SEMA_MAX_K) for one device-resident query; out_keys or res_* may be null
 int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64_t *out_keys, uint64_t *res_ids,
-               float *res_scores, uint32_t *res_nfound, const sema::Exchange *x = nullptr, unsigned flags = 0);
+               float *res_scores, uint32_t *res_nfound, const sema::Exchange *x = nullptr, unsigned flags = 0,
+               uint64_t host_ticket = 0);
 // Host-query fast path (single fused pass on the TMA kernel): the query rides in the kernel
 // parameters and the last block writes the result block + a completion flag straight into mapped
 // host memory, so a search costs one launch and no copies.  host_query_ok: does this handle /
 // k take that path?  host_query_run: launch (x = optional shard exchange) and wait; fills the outputs.
 bool host_query_ok(const sema_index *s, uint32_t k);
+// launch for ticket `ticket` (results + flag go to slot ticket % RES_SLOTS); does not wait
+int host_query_launch(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const sema::Exchange *x, uint64_t ticket);
+// wait for the ticket's flag and copy the slot out
+int host_query_wait(sema_index *s, uint64_t ticket, uint32_t k, uint64_t *row_ids, float *scores, uint32_t *n_found);
 int host_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const sema::Exchange *x,
                    uint64_t *row_ids, float *scores, uint32_t *n_found);
+// ticket bookkeeping shared by the index-level and the shard-group submit / collect entry points
+int slot_claim(sema_index *s, uint32_t k, uint64_t *ticket);                    // next ticket; fails when its slot is still uncollected
+int slot_collect(sema_index *s, uint64_t ticket, uint64_t *row_ids, float *scores, uint32_t *n_found);
 // api_batch.cu: nq device-resident queries (nq x dim dense); K3 when the shape allows, else K2 per query
 int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
                uint32_t *nf_d);

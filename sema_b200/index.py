@@ -172,6 +172,29 @@ class GpuIndex:
         check(self._L.sema_index_search(self._h, q_ptr, k, ids_ptr, sc_ptr, C.byref(nf)))
         return nf.value
 
+    def submit_ptr(self, q_ptr: C.c_void_p, k: int) -> int:
+        """Asynchronous search (``sema_index_search_submit``): returns a ticket once the scan is enqueued."""
+        t = C.c_uint64()
+        check(self._L.sema_index_search_submit(self._h, q_ptr, k, C.byref(t)))
+        return t.value
+
+    def collect_ptr(self, ticket: int, ids_ptr: C.c_void_p, sc_ptr: C.c_void_p) -> int:
+        nf = C.c_uint32()
+        check(self._L.sema_index_search_collect(self._h, ticket, ids_ptr, sc_ptr, C.byref(nf)))
+        return nf.value
+
+    def submit(self, q: np.ndarray, k: int) -> int:
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.shape != (self.dim,):
+            raise ValueError(f"query must be [{self.dim}], got {q.shape}")
+        return self.submit_ptr(_ptr(q), k)          # q is consumed before submit returns
+
+    def collect(self, ticket: int, k: int):
+        ids = np.zeros(max(k, 1), dtype=np.uint64)
+        sc = np.zeros(max(k, 1), dtype=np.float32)
+        nf = self.collect_ptr(ticket, _ptr(ids), _ptr(sc))
+        return ids[:nf].copy(), sc[:nf].copy()
+
     def search_batch(self, Q: np.ndarray, k: int):
         """-> (row_ids uint64[nq,k], scores float32[nq,k], n_found uint32[nq])."""
         Q = np.ascontiguousarray(Q, dtype=np.float32)
@@ -331,6 +354,16 @@ class ShardGroup:
     def search_ptr(self, q_ptr: C.c_void_p, k: int, ids_ptr: C.c_void_p, sc_ptr: C.c_void_p) -> int:
         nf = C.c_uint32()
         check(self._L.sema_shard_group_search(self._g, q_ptr, k, ids_ptr, sc_ptr, C.byref(nf)))
+        return nf.value
+
+    def submit_ptr(self, q_ptr: C.c_void_p, k: int) -> int:
+        t = C.c_uint64()
+        check(self._L.sema_shard_group_search_submit(self._g, q_ptr, k, C.byref(t)))
+        return t.value
+
+    def collect_ptr(self, ticket: int, ids_ptr: C.c_void_p, sc_ptr: C.c_void_p) -> int:
+        nf = C.c_uint32()
+        check(self._L.sema_shard_group_search_collect(self._g, ticket, ids_ptr, sc_ptr, C.byref(nf)))
         return nf.value
 
     def search_device(self, q_ptr: int, k: int, ids_ptr: int, scores_ptr: int, nfound_ptr: int) -> None:

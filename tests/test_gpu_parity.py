@@ -1070,3 +1070,86 @@ def test_sharded_searcher_batch_world1(sema, oracle_c):
     for i in range(nq):
         r_ids, r_sc = oracle_c.scan(X, Q[i], k, id_base=500)
         O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+
+
+# ---------------------------------------------------------------- asynchronous host searches (submit / collect)
+def test_submit_collect_matches_synchronous_search(sema, oracle_c):
+    n, d, k = 50011, 384, 10
+    X = _unit(1, n, d)
+    Q = _unit(2, 40, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        want = [idx.search(q, k) for q in Q]
+        # depth-2 pipeline: submit i+1 before collecting i
+        got = []
+        t_prev = idx.submit(Q[0], k)
+        for i in range(1, len(Q)):
+            t = idx.submit(Q[i], k)
+            got.append(idx.collect(t_prev, k))
+            t_prev = t
+        got.append(idx.collect(t_prev, k))
+        for (a, b), (c, e) in zip(got, want):
+            assert np.array_equal(a, c) and np.array_equal(b, e)
+        r_ids, r_sc = oracle_c.scan(X, Q[5], k)
+        O.check_parity(got[5][0], got[5][1], r_ids, r_sc)
+        # eight in flight, collected out of order; the ninth submit is refused until a slot is free
+        tickets = [idx.submit(Q[i], k) for i in range(8)]
+        with pytest.raises(sema.SemaError):
+            idx.submit(Q[8], k)
+        with pytest.raises(sema.SemaError):
+            idx.search(Q[8], k)                          # the synchronous call needs a slot too
+        for i in (3, 0, 7, 1, 2, 6, 5, 4):
+            a, b = idx.collect(tickets[i], k)
+            assert np.array_equal(a, want[i][0]) and np.array_equal(b, want[i][1])
+        with pytest.raises(sema.SemaError):
+            idx.collect(tickets[0], k)                   # not outstanding any more
+        a, b = idx.search(Q[8], k)
+        assert np.array_equal(a, want[8][0])
+
+
+def test_submit_collect_outside_the_fast_path_and_on_an_empty_index(sema, oracle_c):
+    # dim 130 (generic kernel), k > 128 (multi-pass) and an empty index answer synchronously inside submit
+    X = _unit(1, 3000, 130)
+    Q = _unit(2, 3, 130)
+    with sema.GpuIndex(130, 3000) as idx:
+        t0 = idx.submit(Q[0], 10)
+        assert idx.collect(t0, 10)[0].size == 0          # nothing appended yet
+        idx.append(X, normalize=False)
+        ts = [idx.submit(q, 10) for q in Q]
+        for q, t in zip(Q, ts):
+            ids, sc = idx.collect(t, 10)
+            r_ids, r_sc = oracle_c.scan(X, q, 10)
+            O.check_parity(ids, sc, r_ids, r_sc)
+    X = _unit(1, 5000, 384)
+    with sema.GpuIndex(384, 5000) as idx:
+        idx.append(X, normalize=False)
+        q = _unit(2, 1, 384)[0]
+        t = idx.submit(q, 300)
+        ids, sc = idx.collect(t, 300)
+        r_ids, r_sc = oracle_c.scan(X, q, 300)
+        O.check_parity(ids, sc, r_ids, r_sc)
+
+
+def test_shard_group_submit_collect_world1(sema, oracle_c):
+    import ctypes as C
+    n, d, k = 30000, 384, 10
+    X = _unit(1, n, d)
+    Q = _unit(2, 12, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.set_row_base(100)
+        idx.append(X, normalize=False)
+        g = sema.ShardGroup(idx, 1, 0)
+        try:
+            ids_h, sc_h = np.zeros(k, np.uint64), np.zeros(k, np.float32)
+            tickets = [g.submit_ptr(C.c_void_p(Q[i].ctypes.data), k) for i in range(4)]
+            for i in range(4, 12):
+                tickets.append(g.submit_ptr(C.c_void_p(Q[i].ctypes.data), k))
+                nf = g.collect_ptr(tickets[i - 4], C.c_void_p(ids_h.ctypes.data), C.c_void_p(sc_h.ctypes.data))
+                r_ids, r_sc = oracle_c.scan(X, Q[i - 4], k, id_base=100)
+                O.check_parity(ids_h[:nf].copy(), sc_h[:nf].copy(), r_ids, r_sc)
+            for i in range(8, 12):
+                nf = g.collect_ptr(tickets[i], C.c_void_p(ids_h.ctypes.data), C.c_void_p(sc_h.ctypes.data))
+                r_ids, r_sc = oracle_c.scan(X, Q[i], k, id_base=100)
+                O.check_parity(ids_h[:nf].copy(), sc_h[:nf].copy(), r_ids, r_sc)
+        finally:
+            g.close()
