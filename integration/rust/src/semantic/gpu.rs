@@ -19,6 +19,9 @@ extern "C" {
     fn sema_index_compact(idx: *mut SemaIndex, new_row_of_old: *mut u64, n_live: *mut u64) -> c_int;
     fn sema_index_search(idx: *mut SemaIndex, q: *const f32, k: u32, row_ids: *mut u64, scores: *mut f32,
                          n_found: *mut u32) -> c_int;
+    fn sema_index_search_submit(idx: *mut SemaIndex, q: *const f32, k: u32, ticket: *mut u64) -> c_int;
+    fn sema_index_search_collect(idx: *mut SemaIndex, ticket: u64, row_ids: *mut u64, scores: *mut f32,
+                                 n_found: *mut u32) -> c_int;
     fn sema_index_search_batch(idx: *mut SemaIndex, q: *const f32, nq: u32, k: u32, row_ids: *mut u64,
                                scores: *mut f32, n_found: *mut u32) -> c_int;
     fn sema_mean_pool(idx: *mut SemaIndex, tokens: *const f32, mask: *const f32, n: u64, seq_len: u32,
@@ -67,6 +70,21 @@ impl GpuIndex {
         anyhow::ensure!(q.len() == self.dim, "query has {} dims, index has {}", q.len(), self.dim);
         let (mut ids, mut sc, mut nf) = (vec![0u64; limit.max(1)], vec![0f32; limit.max(1)], 0u32);
         check(unsafe { sema_index_search(self.raw, q.as_ptr(), limit as u32, ids.as_mut_ptr(), sc.as_mut_ptr(), &mut nf) })?;
+        Ok(ids.into_iter().zip(sc).take(nf as usize).collect())
+    }
+
+    /// Asynchronous search: enqueue now (q is consumed before this returns), `collect` later.  Up to 8
+    /// tickets may be outstanding; consecutive scans overlap on the device.
+    pub fn submit(&mut self, q: &[f32], limit: usize) -> anyhow::Result<u64> {
+        anyhow::ensure!(q.len() == self.dim, "query has {} dims, index has {}", q.len(), self.dim);
+        let mut ticket = 0u64;
+        check(unsafe { sema_index_search_submit(self.raw, q.as_ptr(), limit as u32, &mut ticket) })?;
+        Ok(ticket)
+    }
+
+    pub fn collect(&mut self, ticket: u64, limit: usize) -> anyhow::Result<Vec<(u64, f32)>> {
+        let (mut ids, mut sc, mut nf) = (vec![0u64; limit.max(1)], vec![0f32; limit.max(1)], 0u32);
+        check(unsafe { sema_index_search_collect(self.raw, ticket, ids.as_mut_ptr(), sc.as_mut_ptr(), &mut nf) })?;
         Ok(ids.into_iter().zip(sc).take(nf as usize).collect())
     }
 

@@ -76,6 +76,19 @@ int main(void)
         CHECK(sema_index_search(idx, qn, 10, ids, sc, &nf));
         if (nf != 10 || ids[0] != 77 || fabsf(sc[0] - 1.0f) > 1e-5f) return 1;
     }
+    /* asynchronous form: two searches in flight, collected in order */
+    {
+        uint64_t t0 = 0, t1 = 0;
+        static float q2[DIM];
+        CHECK(sema_index_read_rows(idx, 4321, 1, q2));
+        CHECK(sema_index_search_submit(idx, qn, 10, &t0));
+        CHECK(sema_index_search_submit(idx, q2, 10, &t1));
+        CHECK(sema_index_search_collect(idx, t0, ids, sc, &nf));
+        if (nf != 10 || ids[0] != 77) return 1;
+        CHECK(sema_index_search_collect(idx, t1, ids, sc, &nf));
+        if (nf != 10 || ids[0] != 4321) return 1;
+        if (sema_index_search_collect(idx, t1, ids, sc, &nf) != SEMA_ERR_INVALID) return 1; /* already collected */
+    }
     /* mean_pool (kernel K0, src/semantic/embeddings.rs:61-91): 3 tokens, the last one padding */
     {
         static float tok[3 * DIM], pooled[DIM], want[DIM];
