@@ -60,3 +60,25 @@ def test_argument_validation_without_gpu():
     assert L.sema_index_create(0, 384, 1 << 33, 0, C.byref(h)) == _lib.SEMA_ERR_INVALID
     assert L.sema_index_destroy(None) == _lib.SEMA_OK
     assert L.sema_index_size(None) == 0
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    # every entry point added for query streams / async searches / mean-pool / growable indexes rejects
+    # null handles before touching CUDA, and the growable create has no CPU fallback either
+    L = _lib.lib()
+    t = C.c_uint64()
+    nf = C.c_uint32()
+    inv = _lib.SEMA_ERR_INVALID
+    assert L.sema_index_search_submit(None, None, 10, C.byref(t)) == inv
+    assert L.sema_index_search_collect(None, 1, None, None, C.byref(nf)) == inv
+    assert L.sema_index_search_stream_device(None, None, 4, 10, None, None, None) == inv
+    assert L.sema_index_search_batch_keys_device(None, None, 4, 10, None) == inv
+    assert L.sema_topk_merge_batch_device(None, None, 2, 4, 10, None, None, None) == inv
+    assert L.sema_mean_pool(None, None, None, 1, 16, 0, None) == inv
+    assert L.sema_mean_pool_device(None, None, None, 1, 16, 0, None) == inv
+    assert L.sema_shard_group_search_submit(None, None, 10, C.byref(t)) == inv
+    assert L.sema_shard_group_search_stream_device(None, None, 4, 10, None, None, None) == inv
+    h = C.c_void_p()
+    assert L.sema_index_create_growable(0, 384, 0, 0, C.byref(h)) == inv
+    if L.sema_device_count() == 0:
+        assert L.sema_index_create_growable(0, 384, 1000, 0, C.byref(h)) == _lib.SEMA_ERR_CUDA and not h.value
