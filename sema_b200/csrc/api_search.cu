@@ -270,6 +270,33 @@ int host_query_wait(sema_index *s, uint64_t ticket, uint32_t k, uint64_t *row_id
     return SEMA_OK;
 }
 
+// The general host-buffer path (any dim, any k <= SEMA_MAX_K, optional K1 on the query): the query
+// is staged through pinned memory and copied to the device, the result block comes back with a D2H
+// copy, the stream is synchronised.
+int staged_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const Exchange *x, uint64_t *row_ids,
+                     float *scores, uint32_t *n_found)
+{
+    memcpy(s->q_pin, q_host, s->dim * sizeof(float));
+    CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (s->normalize_queries) {
+        int rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
+        if (rc) return rc;
+    }
+    uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
+    float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
+    int rc = scan_query(s, s->q_dev, n, k, nullptr, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev), x);
+    if (rc) return rc;
+    const size_t bytes = 8 + 12 * (size_t)k;
+    CK(cudaMemcpyAsync(s->res_pin, s->res_dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const uint32_t nf = *reinterpret_cast<uint32_t *>(s->res_pin);
+    if (nf == 0xffffffffu) return fail(SEMA_ERR_CUDA, "shard exchange timed out: a rank did not take part in the search");
+    *n_found = nf;
+    memcpy(row_ids, s->res_pin + 8, nf * sizeof(uint64_t));
+    memcpy(scores, s->res_pin + 8 + 8 * (size_t)k, nf * sizeof(float));
+    return SEMA_OK;
+}
+
 int slot_claim(sema_index *s, uint32_t k, uint64_t *ticket)
 {
     const uint64_t t = s->host_seq + 1;
@@ -334,24 +361,7 @@ int sema_index_search(sema_index *s, const float *q, uint32_t k, uint64_t *row_i
     *n_found = 0;
     if (k == 0 || n == 0) return SEMA_OK;
     if (host_query_ok(s, k)) return host_query_run(s, q, (uint32_t)n, k, nullptr, row_ids, scores, n_found);
-    memcpy(s->q_pin, q, s->dim * sizeof(float));
-    CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    if (s->normalize_queries) {
-        rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
-        if (rc) return rc;
-    }
-    uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
-    float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
-    rc = scan_query(s, s->q_dev, (uint32_t)n, k, nullptr, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev));
-    if (rc) return rc;
-    const size_t bytes = 8 + 12 * (size_t)k;
-    CK(cudaMemcpyAsync(s->res_pin, s->res_dev, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    const uint32_t nf = *reinterpret_cast<uint32_t *>(s->res_pin);
-    *n_found = nf;
-    memcpy(row_ids, s->res_pin + 8, nf * sizeof(uint64_t));
-    memcpy(scores, s->res_pin + 8 + 8 * (size_t)k, nf * sizeof(float));
-    return SEMA_OK;
+    return staged_query_run(s, q, (uint32_t)n, k, nullptr, row_ids, scores, n_found);
 }
 
 int sema_index_search_submit(sema_index *s, const float *q, uint32_t k, uint64_t *ticket)

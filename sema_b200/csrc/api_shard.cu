@@ -127,30 +127,15 @@ int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uin
     if (rc) return rc;
     const uint64_t n = s->n_visible;
     s->last_snapshot = n;
+    const bool fast = host_query_ok(s, k);
+    // refuse before the sequence number moves: a rank that skips a search would leave its peers waiting
+    if (fast && s->slots[(s->host_seq + 1) % RES_SLOTS].ticket != 0)
+        return fail(SEMA_ERR_INVALID, "%d searches are already in flight on this handle: collect one first", RES_SLOTS);
     Exchange x;
     group_exchange(g, x);
     x.seq = ++g->seq;
-    if (host_query_ok(s, k)) return host_query_run(s, q, (uint32_t)n, k, &x, row_ids, scores, n_found);
-    memcpy(s->q_pin, q, s->dim * sizeof(float));
-    CK(cudaMemcpyAsync(s->q_dev, s->q_pin, s->ld * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    if (s->normalize_queries) {
-        rc = normalize_queries_dev(s, s->q_dev, s->ld, 1);
-        if (rc) return rc;
-    }
-    uint64_t *ids_d = reinterpret_cast<uint64_t *>(s->res_dev + 8);
-    float *sc_d = reinterpret_cast<float *>(s->res_dev + 8 + 8 * (size_t)k);
-    rc = scan_query(s, s->q_dev, (uint32_t)n, k, nullptr, ids_d, sc_d, reinterpret_cast<uint32_t *>(s->res_dev), &x);
-    if (rc) return rc;
-    const size_t bytes = 8 + 12 * (size_t)k;
-    CK(cudaMemcpyAsync(s->res_pin, s->res_dev, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    const uint32_t nf = *reinterpret_cast<uint32_t *>(s->res_pin);
-    if (nf == 0xffffffffu) return fail(SEMA_ERR_CUDA, "shard exchange timed out: a rank did not take part in search %llu",
-                                       (unsigned long long)g->seq);
-    *n_found = nf;
-    memcpy(row_ids, s->res_pin + 8, nf * sizeof(uint64_t));
-    memcpy(scores, s->res_pin + 8 + 8 * (size_t)k, nf * sizeof(float));
-    return SEMA_OK;
+    if (fast) return host_query_run(s, q, (uint32_t)n, k, &x, row_ids, scores, n_found);
+    return staged_query_run(s, q, (uint32_t)n, k, &x, row_ids, scores, n_found);
 }
 
 int sema_shard_group_search_submit(sema_shard_group *g, const float *q, uint32_t k, uint64_t *ticket)

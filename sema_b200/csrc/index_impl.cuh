@@ -157,6 +157,9 @@ int host_query_launch(sema_index *s, const float *q_host, uint32_t n, uint32_t k
 int host_query_wait(sema_index *s, uint64_t ticket, uint32_t k, uint64_t *row_ids, float *scores, uint32_t *n_found);
 int host_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const sema::Exchange *x,
                    uint64_t *row_ids, float *scores, uint32_t *n_found);
+// the general host-buffer path: query staged through pinned memory + H2D, result D2H, stream sync
+int staged_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const sema::Exchange *x,
+                     uint64_t *row_ids, float *scores, uint32_t *n_found);
 // ticket bookkeeping shared by the index-level and the shard-group submit / collect entry points
 int slot_claim(sema_index *s, uint32_t k, uint64_t *ticket);                    // next ticket; fails when its slot is still uncollected
 int slot_collect(sema_index *s, uint64_t ticket, uint64_t *row_ids, float *scores, uint32_t *n_found);
