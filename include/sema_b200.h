@@ -268,7 +268,8 @@ int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float 
 /* Tuning knob for measurements (results never change).  0 = default K2 kernel (TMA bulk-copy ring
  * for dim 384 / 768), 1 / 2 / 3 = the register-fed K2 kernel with 4 / 2 / 8 rows per warp batch;
  * 100 + c = K3 cluster size c (0 = automatic); 200 / 201 = K3 two / one query tiles per CTA in the
- * single-pass stage; 300 + d = K3 timing probes (wrong results, timing only); 400 / 401 = K3
+ * single-pass stage; 300 + d = K3 timing probes (d = 1..3: wrong results, timing only; 8 = epilogue
+ * without its group early-out, correct results); 400 / 401 = K3
  * single-pass candidate lists of 32 / 16 for k <= 10; 500 / 501 = host searches staged through
  * H2D + D2H copies / query by kernel parameter + results to mapped host memory (default);
  * 600 / 601 = query streams unchained / chained (default); negative = query.  Returns the value set. */

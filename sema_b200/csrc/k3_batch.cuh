@@ -157,6 +157,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
         : "memory");
 }
 
+// three-input maximum (one instruction on sm_100: FMNMX3); a NaN operand is ignored
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ---------------------------------------------------------------- plane builder
 // X (fp32, row stride ld) rows [row_begin, row_end) -> pre-tiled bf16 hi/lo planes.
 // One thread per (row, 8-element k-chunk); consecutive threads write consecutive 16 B.
@@ -210,7 +218,7 @@ struct Params {
     uint32_t n_tiles;             // ceil(n_rows / 64)
     uint32_t parts;               // row partitions (gridDim.y)
     uint32_t dim;
-    uint32_t debug;               // timing experiments only (wrong results): see the epilogue
+    uint32_t debug;               // timing experiments only: 1-3 give wrong results, 8 = no group early-out (correct); see the epilogue
 };
 
 // PASSES = 3: bf16x3 split (hi.hi + lo.hi + hi.lo), a stage holds the hi and lo plane blocks.
@@ -417,13 +425,30 @@ batch_scan_kernel(const Params p)
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);   // MMA may overwrite this accumulator
                 const uint32_t row0 = t * TILE_N;
                 if (p.debug == 1) continue;                       // probe: no scan at all
-                // Pass 1 (unrolled, branch-free): which of my 64 scores beat the admission threshold?
+                // Pass 0: the maximum of each group of 16 scores (8 three-input maxima per group).  Once the
+                // lists have warmed up almost no group holds a score above the admission threshold, and a
+                // group nobody in the warp needs is skipped: the epilogue's instruction issue is energy the
+                // power-capped tensor pipe does not get.  (Padding rows of the last tile can only make a
+                // group look interesting, never hide a survivor; NaN scores are ignored by max and by >.)
+                // Pass 1 (per group, warp-uniform): which of my scores beat the admission threshold?
                 uint32_t mask[2] = {0u, 0u};
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int g = 0; g < 4; ++g) {
+                    const int h = g >> 1, c0 = (g & 1) * 16;
+                    bool scan = true;
+                    if (!(p.debug & 8)) {                            // debug 8: every group is scanned (A/B baseline)
+                        float mx = fmaxf(__uint_as_float(r[h][c0]), __uint_as_float(r[h][c0 + 1]));
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        mask[h] |= (__uint_as_float(r[h][c]) > thr) ? (1u << c) : 0u;
+                        for (int c = 2; c < 16; c += 2)
+                            mx = fmax3(mx, __uint_as_float(r[h][c0 + c]), __uint_as_float(r[h][c0 + c + 1]));
+                        scan = __any_sync(FULL, mx > thr);
+                    }
+                    if (scan) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            mask[h] |= (__uint_as_float(r[h][c0 + c]) > thr) ? (1u << (c0 + c)) : 0u;
+                    }
+                }
                 const uint32_t live = p.n_rows - row0;           // rows of this tile that exist (>= 1)
                 if (live < 32) { mask[0] &= (1u << live) - 1u; mask[1] = 0u; }
                 else if (live < 64) mask[1] &= (1u << (live - 32)) - 1u;
