@@ -154,8 +154,10 @@ int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row
 int sema_index_search_submit(sema_index *idx, const float *q, uint32_t k, uint64_t *ticket);
 int sema_index_search_collect(sema_index *idx, uint64_t ticket, uint64_t *row_ids, float *scores,
                               uint32_t *n_found);
-/* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq].  With the
- * cosine metric, dim % 64 == 0, dim <= 768, k <= 100 and nq >= 4 this runs kernel K3 (tcgen05
+/* nq queries (Q: nq x dim row-major); outputs nq x k row-major, n_found[nq].  With
+ * dim % 64 == 0, dim <= 768, k <= 100, nq >= 4 and either the cosine metric or the L2 metric over
+ * rows of (nearly) constant norm — the reference's case: unit-norm rows under LanceDB's default
+ * squared-L2 `_distance` — this runs kernel K3 (tcgen05
  * tensor cores, bf16 split precision — see sema_index_set_batch_mode — with exact fp32
  * re-scoring of the candidates; needs a second dim*4 bytes per row of HBM for the bf16 planes,
  * built on first use); otherwise, or if that memory cannot be had, K2 runs once per query.

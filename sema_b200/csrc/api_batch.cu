@@ -17,10 +17,24 @@ constexpr float K3_ERR_REL_1PASS = 8.5e-3f;  // >= 2*2^-8 + 2^-16 (both operands
 // filter up to dim 768 (q_hi only) or when asked for (batch mode 3); 0 = K3 cannot serve this shape
 int k3_passes(const sema_index *s, uint32_t k)
 {
-    if (s->metric != SEMA_METRIC_COSINE || s->dim % k3::BLOCK_K != 0 || k > K3_MAX_K || s->planes_failed) return 0;
+    if (s->dim % k3::BLOCK_K != 0 || k > K3_MAX_K || s->planes_failed) return 0;
+    if (s->metric == SEMA_METRIC_L2 && !s->l2_norms_constant) return 0;   // see k3_check_norms
     if (s->dim <= (uint32_t)k3::MAX_DIM) return s->batch_mode == 3 ? 1 : 3;
     if (s->dim <= (uint32_t)k3::MAX_DIM_1PASS) return 1;
     return 0;
+}
+
+// L2 metric: K3 selects candidates by dot product, which ranks like the distance only when the row
+// norms are (nearly) constant — the reference's case, every stored vector is unit-norm
+// (src/semantic/embeddings.rs:83-88).  K1 tracks [max, min] |x|^2; anything else stays on K2.
+int k3_check_norms(sema_index *s)
+{
+    if (s->metric != SEMA_METRIC_L2) return SEMA_OK;
+    float mm[2] = {0.0f, 0.0f};
+    CK(cudaMemcpyAsync(mm, s->max_norm2, sizeof mm, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->l2_norms_constant = mm[1] > 0.0f && mm[0] < __builtin_inff() && (mm[0] - mm[1]) <= 1e-3f * mm[0];
+    return SEMA_OK;
 }
 
 // Bring the bf16 planes up to date with rows [0, n).  Tombstones invalidate from their row on.
@@ -233,9 +247,15 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         r.row_base = s->row_base;
         r.max_norm2 = s->max_norm2;
         r.err_rel = passes == 1 ? K3_ERR_REL_1PASS : K3_ERR_REL;
-        if (k <= 32) k3::rescore_kernel<1><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
-        else if (k <= 64) k3::rescore_kernel<2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
-        else k3::rescore_kernel<4><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        if (s->metric == SEMA_METRIC_L2) {
+            if (k <= 32) k3::rescore_kernel<1, METRIC_L2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+            else if (k <= 64) k3::rescore_kernel<2, METRIC_L2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+            else k3::rescore_kernel<4, METRIC_L2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        } else {
+            if (k <= 32) k3::rescore_kernel<1, METRIC_COSINE><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+            else if (k <= 64) k3::rescore_kernel<2, METRIC_COSINE><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+            else k3::rescore_kernel<4, METRIC_COSINE><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
+        }
         CK(cudaGetLastError());
         s->launches++;
     }
@@ -321,6 +341,10 @@ int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t
                uint32_t *nf_d)
 {
     const bool want_k3 = s->batch_mode >= 2 || (s->batch_mode == 0 && nq >= 4);
+    if (want_k3) {
+        int rc = k3_check_norms(s);
+        if (rc) return rc;
+    }
     if (want_k3 && k3_passes(s, k) != 0) {
         int rc = k3_sync_planes(s, n);
         if (rc == SEMA_OK) return k3_batch(s, Qd, nq, n, k, ids_d, sc_d, nf_d);

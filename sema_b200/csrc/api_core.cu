@@ -216,9 +216,12 @@ static int create_impl(int device, uint32_t dim, uint64_t capacity_rows, int met
     CKD(cudaMalloc(&s->ticket, 4 * sizeof(unsigned int)));
     CKD(cudaMemset(s->ticket, 0, 4 * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
-    CKD(cudaMalloc(&s->max_norm2, sizeof(float)));
+    CKD(cudaMalloc(&s->max_norm2, 2 * sizeof(float)));
     CKD(cudaMalloc(&s->qscratch, 65536 + 32));
-    CKD(cudaMemset(s->max_norm2, 0, sizeof(float)));
+    {
+        const float init[2] = {0.0f, __builtin_inff()};   // [max |x|^2, min |x|^2] over the rows K1 has seen
+        CKD(cudaMemcpy(s->max_norm2, init, sizeof init, cudaMemcpyHostToDevice));
+    }
     CKD(cudaMalloc(&s->res_dev, res_bytes));
     CKD(cudaHostAlloc(&s->res_pin, res_bytes, cudaHostAllocPortable));
     // mapped result block of the host-query path: the kernel stores results + completion flag here

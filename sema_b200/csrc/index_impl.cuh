@@ -103,7 +103,7 @@ struct sema_index {
     int variant = 0;
     uint64_t launches = 0;
     // ---- K3 (batched tensor-core path) state
-    float *max_norm2 = nullptr;         // device: max squared row norm (written by K1)
+    float *max_norm2 = nullptr;         // device: [max, min] squared row norm over the rows K1 has seen
     unsigned char *planes = nullptr;    // pre-tiled bf16 hi/lo planes, built lazily
     uint64_t planes_rows = 0;           // rows [0, planes_rows) are reflected in the planes
     bool planes_failed = false;         // allocation failed once: stay on the K2 loop
@@ -117,6 +117,7 @@ struct sema_index {
     int k3_debug = 0;                   // timing experiments only (wrong results): see k3::Params::debug
     int k3_kc16 = 1;                    // single-pass stage with k <= 10 keeps 16 candidates per list (0 = 32) — tuning
     int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
+    bool l2_norms_constant = false;     // L2 metric: row norms nearly constant, so K3's dot-product selection ranks like the distance
     int normalize_queries = 0;          // apply K1 to host queries before scanning
     unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch][K0 text counters: +8 query stream, +16 ingest stream]
     uint64_t k3_queries = 0, k3_fallbacks = 0, k3_cascaded = 0;

@@ -100,8 +100,12 @@ ingest_kernel(const float *src, uint64_t src_ld, float *dst, uint32_t ld, uint32
         __syncwarp();
         if (lane == 0) {
             valid_out[r] = ok ? 1 : 0;
-            // non-negative floats order like unsigned ints; K3 uses this to bound |x|
-            if (ok) atomicMax(reinterpret_cast<unsigned int *>(max_norm2), __float_as_uint(scale ? 1.0000005f : ss));
+            // non-negative floats order like unsigned ints; K3 uses max_norm2[0] = max |x|^2 to bound its
+            // error and max_norm2[1] = min |x|^2 (L2 metric: how far the dot product is from the distance)
+            if (ok) {
+                atomicMax(reinterpret_cast<unsigned int *>(max_norm2), __float_as_uint(scale ? 1.0000005f : ss));
+                atomicMin(reinterpret_cast<unsigned int *>(max_norm2) + 1, __float_as_uint(scale ? 0.9999995f : ss));
+            }
         }
     }
 }

@@ -521,13 +521,19 @@ struct RescoreParams {
     uint32_t *res_nfound;      // [nq]
     uint32_t *flags;           // [nq] 1 = exactness not proven, re-run through K2
     uint32_t ld4, dim, k, parts, kc, row_base;
-    const float *max_norm2;    // device: max squared row norm seen by K1 (bounds |x|)
+    const float *max_norm2;    // device: [max, min] squared row norm seen by K1 (bounds |x|)
     float err_rel;             // |tensor-core score - exact score| <= err_rel * |q| * max|x|
 };
+// METRIC_L2: the tensor-core pass still selects by dot product (the planes hold x, the queries q);
+// the candidates are re-scored with K2's squared-L2 arithmetic and ranked by ascending distance.
+// |q - x|^2 = |q|^2 + |x|^2 - 2 q.x, so a row outside partition P's list (dot <= thr_P + err) has
+// distance >= |q|^2 + min|x|^2 - 2 (thr_P + err): the proof needs the k-th exact distance below that.
+// With unit-norm rows (the reference's case) the two rankings coincide and the proof is as tight as
+// for the cosine metric; the host only takes this path when the row norms are (nearly) constant.
 
 // One block per query: every candidate is re-scored with K2's fp32 arithmetic (lane-strided
 // float4 FMAs + butterfly), ranked by (score, lower row id) and emitted.
-template <int M>
+template <int M, int METRIC>
 __global__ void __launch_bounds__(SCAN_THREADS)
 rescore_kernel(const RescoreParams p)
 {
@@ -545,16 +551,16 @@ rescore_kernel(const RescoreParams p)
         if (row == 0xffffffffu) continue;  // warp-uniform
         const float4 *xp = p.X + (size_t)row * p.ld4;
         float acc = 0.0f;
-        for (uint32_t v = lane; v < nv; v += 32) acc = accum4<METRIC_COSINE>(acc, xp[v], qp[v]);
+        for (uint32_t v = lane; v < nv; v += 32) acc = accum4<METRIC>(acc, xp[v], qp[v]);
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
-        const uint64_t key = make_key(acc, p.row_base + row);
+        const uint64_t key = make_key(METRIC == METRIC_L2 ? -acc : acc, p.row_base + row);
         top.offer(key, lane == 0 && acc == acc, lane, k);
     }
     block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
     if (warp == 0) {
-        emit_results<M, METRIC_COSINE>(top, k, nullptr, p.res_ids + (size_t)q * k, p.res_scores + (size_t)q * k,
-                                       p.res_nfound + q, lane);
+        emit_results<M, METRIC>(top, k, nullptr, p.res_ids + (size_t)q * k, p.res_scores + (size_t)q * k,
+                                p.res_nfound + q, lane);
         // exactness proof: rows outside partition P's list have approx score <= thr_P, hence
         // exact score <= thr_P + err_bound; the k-th exact score must beat that for every P.
         float worst = -INFINITY;
@@ -572,9 +578,14 @@ rescore_kernel(const RescoreParams p)
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) qq += __shfl_xor_sync(FULL, qq, d);
         if (lane == 0) {
-            const float err_bound = p.err_rel * sqrtf(qq) * sqrtf(*p.max_norm2);
+            const float err_bound = p.err_rel * sqrtf(qq) * sqrtf(p.max_norm2[0]);
             bool proven = true;
-            if (worst > -INFINITY) proven = (kk != 0) && (key_rank(kk) > worst + err_bound);
+            if (worst > -INFINITY) {
+                if (METRIC == METRIC_L2)   // key_rank = -distance; slack for the fp32 evaluation of the bound itself
+                    proven = (kk != 0) && (-key_rank(kk) < (qq + p.max_norm2[1] - 2.0f * (worst + err_bound)) * (1.0f - 1e-6f) - 1e-6f);
+                else
+                    proven = (kk != 0) && (key_rank(kk) > worst + err_bound);
+            }
             p.flags[q] = proven ? 0u : 1u;
         }
     }

@@ -461,7 +461,7 @@ def test_k3_null_rows_appends_and_tombstones(sema, oracle_c):
 
 
 def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
-    # dim 1024 and the L2 metric are served by K2 (one pass per query): same results
+    # dim 1024 is served by K2 (one pass per query); the L2 metric over unit rows by K3: same results
     X = _unit(1, 5000, 1024)
     Q = _unit(2, 9, 1024)
     with sema.GpuIndex(1024, 5000) as idx:
@@ -476,7 +476,7 @@ def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
         idx.append(X, normalize=False)
         Q = _unit(2, 9, 384)
         ids, sc, nf = idx.search_batch(Q, 10)
-        assert idx.batch_stats()[0] == 0
+        assert idx.batch_stats()[0] == 9                  # unit-norm rows: K3 selects by dot product, re-scores as distances
     r = oracle_c.scan_batch(X, Q, 10, metric=1)
     for i in range(9):
         O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
@@ -1153,3 +1153,61 @@ def test_shard_group_submit_collect_world1(sema, oracle_c):
                 O.check_parity(ids_h[:nf].copy(), sc_h[:nf].copy(), r_ids, r_sc)
         finally:
             g.close()
+
+
+# ---------------------------------------------------------------- K3 under the reference's literal metric (squared L2)
+@pytest.mark.parametrize("mode", [0, 2, 3], ids=["cascade", "bf16x3", "bf16x1"])
+def test_k3_l2_metric_on_unit_rows_matches_k2_and_oracle(sema, oracle_c, mode):
+    """LanceDB's default `_distance` (squared L2, ascending; src/storage/lance_indexer.rs:121-126) over the
+    unit-norm rows the reference stores: the tensor-core pass selects by dot product, the candidates are
+    re-scored as exact distances, and the proof accounts for min |x|^2 — same bits as K2's L2 scan."""
+    n, d, k, nq = 40000, 384, 10, 70
+    raw = O.synth(1, 0, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n, metric=1) as idx:
+        idx.append(raw, normalize=True)                   # K1 normalises: every row is unit-norm
+        X = idx.read_rows(0, n)
+        idx.set_batch_mode(mode)
+        ids3, sc3, nf3 = idx.search_batch(Q, k)
+        served, fallbacks = idx.batch_stats()
+        assert served == nq                               # K3 really ran under the L2 metric
+        idx.set_batch_mode(1)
+        ids2, sc2, nf2 = idx.search_batch(Q, k)
+    assert np.array_equal(ids3, ids2) and np.array_equal(sc3, sc2) and np.array_equal(nf3, nf2)
+    assert np.all(np.diff(sc3, axis=1) >= 0)              # ascending distance
+    for i in range(0, nq, 7):
+        r_ids, r_sc = oracle_c.scan(X, Q[i], k, 1)
+        O.check_parity(ids3[i, :nf3[i]], sc3[i, :nf3[i]], r_ids, r_sc)
+    assert fallbacks <= max(1, nq // 20)
+
+
+def test_k3_l2_metric_with_varying_norms_stays_on_k2(sema, oracle_c):
+    # rows of different length: the dot product does not rank like the distance, so batches run K2
+    n, d, k, nq = 20000, 384, 10, 8
+    X = _unit(1, n, d) * np.linspace(0.5, 2.0, n, dtype=np.float32)[:, None]
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n, metric=1) as idx:
+        idx.append(X, normalize=False)
+        idx.set_batch_mode(2)
+        ids, sc, nf = idx.search_batch(Q, k)
+        assert idx.batch_stats()[0] == 0                  # not served by K3
+    for i in range(nq):
+        r_ids, r_sc = oracle_c.scan(X, Q[i], k, 1)
+        O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+
+
+def test_k3_l2_metric_with_a_zero_row_stays_exact(sema, oracle_c):
+    # a zero row (an all-padding text pools to zero) has norm 0: min |x|^2 = 0 disables the dot-product selection
+    n, d, k, nq = 20000, 384, 10, 8
+    raw = O.synth(1, 0, n, d)
+    raw[77] = 0.0
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n, metric=1) as idx:
+        idx.append(raw, normalize=True)
+        X = idx.read_rows(0, n)
+        idx.set_batch_mode(0)
+        ids, sc, nf = idx.search_batch(Q, k)
+        assert idx.batch_stats()[0] == 0
+    for i in range(nq):
+        r_ids, r_sc = oracle_c.scan(X, Q[i], k, 1)
+        O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
