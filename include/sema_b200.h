@@ -149,8 +149,7 @@ int sema_index_search(sema_index *idx, const float *q, uint32_t k, uint64_t *row
  * tickets may be outstanding per handle; they complete in submission order and may be collected in
  * any order.  Consecutive submitted scans are chained on the device (programmatic dependent launch),
  * so with two or more in flight the handle serves host queries at the query-stream rate.  Shapes
- * outside the fast path (dim other than 384 / 768, k > 128, normalised queries) run synchronously
- * inside submit.  sema_index_search(q) == submit(q) + collect. */
+ * outside the fast path (dim other than 384 / 768, k > 128) run synchronously inside submit.  sema_index_search(q) == submit(q) + collect. */
 int sema_index_search_submit(sema_index *idx, const float *q, uint32_t k, uint64_t *ticket);
 int sema_index_search_collect(sema_index *idx, uint64_t ticket, uint64_t *row_ids, float *scores,
                               uint32_t *n_found);
@@ -260,8 +259,9 @@ uint64_t sema_index_capacity(const sema_index *idx);
 uint32_t sema_index_dim(const sema_index *idx);
 int sema_index_device(const sema_index *idx);
 /* on != 0: sema_index_search / _search_batch first apply the mean_pool normalise tail
- * (src/semantic/embeddings.rs:83-88) to the query on the device (kernel K1), as the reference's
- * embedder does for queries and rows alike.  Returns the setting now active (on < 0 = query). */
+ * (src/semantic/embeddings.rs:83-88) to the query on the device, as the reference's embedder does
+ * for queries and rows alike: kernel K1 for batches and the staged path, the same arithmetic in
+ * K2's registers on the host-query path (identical bits either way).  Returns the setting now active (on < 0 = query). */
 int sema_index_set_normalize_queries(sema_index *idx, int on);
 /* snapshot (visible rows) the most recent search on this handle scanned */
 uint64_t sema_index_last_snapshot(const sema_index *idx);

@@ -51,10 +51,19 @@ int normalize_queries_dev(sema_index *s, float *q, uint64_t stride, uint32_t nq)
         uint64_t blocks = ((uint64_t)m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
         if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
         float *base = q + (size_t)done * stride;
-        // generic (scalar) kernel: src == dst, same stride; pad columns [dim, stride) are rewritten as zeros
-        ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(
-            base, stride, base, (uint32_t)stride, s->dim, m, nullptr, s->qscratch,
-            1, reinterpret_cast<float *>(s->qscratch + 65536));
+        // src == dst, same stride; pad columns [dim, stride) are rewritten as zeros.  Dense, aligned
+        // queries take the float4 kernel: the same per-lane partial sums as the stored rows and as
+        // the in-register normalisation of the host-query path (k2_scan_tma.cuh), so every path
+        // produces the same normalised query bit for bit.
+        const bool vec4 = stride == s->dim && (s->dim & 3u) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+        if (vec4)
+            ingest_kernel<true><<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(
+                base, stride, base, (uint32_t)stride, s->dim, m, nullptr, s->qscratch,
+                1, reinterpret_cast<float *>(s->qscratch + 65536));
+        else
+            ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(
+                base, stride, base, (uint32_t)stride, s->dim, m, nullptr, s->qscratch,
+                1, reinterpret_cast<float *>(s->qscratch + 65536));
         CK(cudaGetLastError());
         s->launches++;
     }

@@ -41,6 +41,7 @@ void fill_params(sema_index *s, const ScanArgs &a, ScanParams &p)
     p.work_ctr = nullptr;
     p.host_flag = nullptr;
     p.host_seq = 0;
+    p.normalize_query = 0;
     if (a.x) p.x = *a.x;
     else memset(&p.x, 0, sizeof p.x);
 }
@@ -97,6 +98,7 @@ int run_scan_tma(sema_index *s, const ScanArgs &a)
         p.q = nullptr;
         p.host_flag = reinterpret_cast<uint64_t *>(s->res_map_dev + (a.host_ticket % RES_SLOTS) * RES_SLOT_BYTES + RES_MAP_FLAG_OFF);
         p.host_seq = a.host_ticket;
+        p.normalize_query = s->normalize_queries ? 1u : 0u;
     } else {
         qa.unused = 0;
     }
@@ -223,7 +225,7 @@ int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64
 bool host_query_ok(const sema_index *s, uint32_t k)
 {
     const uint32_t ld4 = s->ld / 4;
-    return s->host_path && s->variant == 0 && !s->normalize_queries && k >= 1 && k <= (uint32_t)K_PASS &&
+    return s->host_path && s->variant == 0 && k >= 1 && k <= (uint32_t)K_PASS &&
            s->ld == s->dim && (ld4 == 96 || ld4 == 192) && s->res_map != nullptr;
 }
 

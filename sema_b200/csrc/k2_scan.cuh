@@ -78,6 +78,10 @@ struct ScanParams {
     // results, so the host can poll instead of issuing a D2H copy and a stream synchronise.
     uint64_t *host_flag;
     uint64_t host_seq;
+    // Query passed by kernel parameter only: apply the mean_pool normalise tail
+    // (src/semantic/embeddings.rs:83-88) to it in registers, with kernel K1's arithmetic and
+    // summation order, so the result is the one K1 would have written.
+    uint32_t normalize_query;
     Exchange x;             // sharded mode (world > 1): fused peer exchange + global merge
 };
 

@@ -120,6 +120,27 @@ scan_topk_tma_kernel(const __grid_constant__ ScanParams p, const __grid_constant
             if constexpr (QP) qv[v] = qa.v[v * 32 + lane];
             else qv[v] = reinterpret_cast<const float4 *>(p.q)[v * 32 + lane];
         }
+        if constexpr (QP) {
+            if (p.normalize_query) {
+                // K1's rule and order: lane l sums its float4 l, l+32, ... element by element (multiply,
+                // then add), butterfly over the lanes; a non-finite query becomes NaN (never matches)
+                float ss = 0.0f;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    ss = __fadd_rn(ss, __fmul_rn(qv[v].x, qv[v].x)); ss = __fadd_rn(ss, __fmul_rn(qv[v].y, qv[v].y));
+                    ss = __fadd_rn(ss, __fmul_rn(qv[v].z, qv[v].z)); ss = __fadd_rn(ss, __fmul_rn(qv[v].w, qv[v].w));
+                }
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL, ss, m);
+                const bool ok = ss <= 3.402823466e+38f;
+                const float norm = sqrtf(ss), qnan = __uint_as_float(0x7fc00000u);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    if (!ok) qv[v] = make_float4(qnan, qnan, qnan, qnan);
+                    else if (norm > 0.0f) { qv[v].x = qv[v].x / norm; qv[v].y = qv[v].y / norm; qv[v].z = qv[v].z / norm; qv[v].w = qv[v].w / norm; }
+                }
+            }
+        }
         const int my_r = row_of_lane<R>(lane);
         const bool rep = (lane & (32 / R - 1)) == 0;
         uint32_t stage = 0, phase = 0;

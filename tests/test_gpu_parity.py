@@ -1211,3 +1211,28 @@ def test_k3_l2_metric_with_a_zero_row_stays_exact(sema, oracle_c):
     for i in range(nq):
         r_ids, r_sc = oracle_c.scan(X, Q[i], k, 1)
         O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+
+
+def test_normalised_host_queries_take_the_fast_path_with_k1_arithmetic(sema, oracle_c):
+    """sema_index_set_normalize_queries(1): the host-query path normalises the query in registers with
+    K1's arithmetic, so it returns the same bits as the staged path (H2D + K1 + K2) and as a batch."""
+    n, d, k = 30011, 384, 10
+    X = _unit(1, n, d)
+    Qraw = O.synth(2, 0, 12, d)                          # un-normalised queries
+    Qraw[3] = 0.0                                        # a zero query stays zero: every score is 0
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        idx.set_normalize_queries(True)
+        fast = [idx.search(q, k) for q in Qraw]
+        idx.set_scan_variant(500)                        # staged path: K1 normalises the query on the device
+        slow = [idx.search(q, k) for q in Qraw]
+        idx.set_scan_variant(501)
+        bids, bsc, bnf = idx.search_batch(Qraw, k)
+    for i, ((a, b), (c, e)) in enumerate(zip(fast, slow)):
+        assert np.array_equal(a, c) and np.array_equal(b, e), i
+        assert np.array_equal(a, bids[i, :bnf[i]]) and np.array_equal(b, bsc[i, :bnf[i]]), i
+    Qn = O.normalize(Qraw)
+    for i in (0, 5, 11):
+        r_ids, r_sc = oracle_c.scan(X, Qn[i], k)
+        O.check_parity(fast[i][0], fast[i][1], r_ids, r_sc)
+    assert not fast[3][1].any()
