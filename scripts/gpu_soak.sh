@@ -14,8 +14,13 @@ for l in open("gpurun_out/soak_n${N}_$tag.log"):
 PY
   tail -2 gpurun_out/soak_n${N}_$tag.log | grep -v "^{" | cut -c1-200
 }
+if [ "${SOAK_SET:-full}" = "short" ]; then      # two runs: tiny shards (exchange-bound) and the bench's own shard size
+run small --rows 400000 --steps 50000 --warmup 20
+run mid --rows 10000000 --steps 5000 --warmup 20
+else
 run tiny --rows 5000 --steps 100000 --warmup 20
 run small --rows 100000 --steps 50000 --warmup 20
 run k50 --rows 300000 --k 50 --steps 20000 --warmup 20
 run mid --rows 1000000 --steps 20000 --warmup 20
 run d768 --rows 500000 --dim 768 --k 100 --steps 10000 --warmup 20
+fi
