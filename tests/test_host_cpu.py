@@ -88,3 +88,29 @@ def test_chunker_restatement_properties():
     assert E.create_chunks("p.md", "short") == []                         # < MIN_CHUNK_SIZE
     for a, b in zip(cs, cs[1:]):                                          # overlapping windows
         assert b["start_line"] <= a["end_line"]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (the CPU search path on the host cores) runs without a GPU and prints one
+    JSON line with the contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-rows", "20000"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert quiet.returncode == 0 and not [l for l in quiet.stdout.splitlines() if l.startswith("{")]
