@@ -18,19 +18,32 @@ int launch_pool(sema_index *s, cudaStream_t stream, const float *tokens_dev, con
         CK(cudaFuncSetAttribute(pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[s->device & 63] = true;
     }
-    // one thread per column, in as many equal passes as the block size allows (dim 768 -> 2 x 384)
-    const uint32_t passes = (s->dim + POOL_MAX_THREADS - 1) / POOL_MAX_THREADS;
-    uint32_t threads = (((s->dim + passes - 1) / passes) + 31u) & ~31u;
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_kernel, (int)threads, smem));
-    if (per_sm < 1) return fail(SEMA_ERR_UNSUPPORTED, "pool kernel does not fit on an SM");
-    uint64_t grid = (uint64_t)s->num_sms * per_sm;          // exactly the resident blocks: texts are claimed dynamically
-    if (grid > n) grid = n;
-    // one counter per stream K0 can run on (pooled appends on the ingest stream, pooled queries on the query stream)
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>(s->qscratch + 65536 + (stream == s->ingest_stream ? 16 : 8));
     CK(cudaMemsetAsync(ctr, 0, sizeof *ctr, stream));
-    pool_kernel<<<(unsigned)grid, threads, smem, stream>>>(tokens_dev, mask_dev, n, seq_len, s->dim, out_dev, out_ld,
-                                                           skip_masked, ctr);
+    // float4 columns when the layout allows (dim 384: 96 threads per text, ~4x more texts resident per SM)
+    const bool v4 = (s->dim & 3u) == 0 && (seq_len & 3u) == 0 && s->dim / 4 <= 256 && smem <= 48 * 1024 &&
+                    (reinterpret_cast<uintptr_t>(tokens_dev) & 15) == 0;
+    if (v4) {
+        const uint32_t threads = ((s->dim / 4) + 31u) & ~31u;
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_kernel_v4, (int)threads, smem));
+        if (per_sm < 1) return fail(SEMA_ERR_UNSUPPORTED, "pool kernel does not fit on an SM");
+        uint64_t grid = (uint64_t)s->num_sms * per_sm;
+        if (grid > n) grid = n;
+        pool_kernel_v4<<<(unsigned)grid, threads, smem, stream>>>(tokens_dev, mask_dev, n, seq_len, s->dim, out_dev, out_ld,
+                                                                  skip_masked, ctr);
+    } else {
+        // one thread per column, in as many equal passes as the block size allows (dim 768 -> 2 x 384)
+        const uint32_t passes = (s->dim + POOL_MAX_THREADS - 1) / POOL_MAX_THREADS;
+        uint32_t threads = (((s->dim + passes - 1) / passes) + 31u) & ~31u;
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_kernel, (int)threads, smem));
+        if (per_sm < 1) return fail(SEMA_ERR_UNSUPPORTED, "pool kernel does not fit on an SM");
+        uint64_t grid = (uint64_t)s->num_sms * per_sm;          // exactly the resident blocks: texts are claimed dynamically
+        if (grid > n) grid = n;
+        pool_kernel<<<(unsigned)grid, threads, smem, stream>>>(tokens_dev, mask_dev, n, seq_len, s->dim, out_dev, out_ld,
+                                                               skip_masked, ctr);
+    }
     CK(cudaGetLastError());
     s->launches++;
     return SEMA_OK;

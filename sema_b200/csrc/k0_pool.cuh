@@ -103,4 +103,97 @@ pool_kernel(const float *tokens, const float *mask, uint64_t n, uint32_t seq, ui
     }
 }
 
+// float4 form for hidden % 4 == 0 (and 16-byte aligned rows): one thread owns four adjacent columns,
+// so a text needs hidden / 4 threads (96 for dim 384) and an SM holds ~4x more texts at once — their
+// serial pieces (mask compaction, the in-order norm) overlap with other texts' loads.  The four
+// columns of a thread are independent sums in token order: the same bits as pool_kernel.
+__global__ void __launch_bounds__(256)
+pool_kernel_v4(const float *tokens, const float *mask, uint64_t n, uint32_t seq, uint32_t hidden, float *out,
+               uint64_t out_ld, int skip_masked, unsigned long long *next_text)
+{
+    extern __shared__ float psm[];
+    float *sm_mask = psm;
+    float *sm_mv = psm + seq;
+    uint32_t *sm_idx = reinterpret_cast<uint32_t *>(psm + 2 * seq);
+    float *sm_pool = psm + 3 * seq;                                // [hidden], 16-byte aligned (seq % 4 == 0 is checked by the host)
+    __shared__ float sm_norm;
+    __shared__ uint32_t sm_cnt;
+    __shared__ unsigned long long sm_text;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t h4 = hidden / 4;
+
+    for (;;) {
+        if (threadIdx.x == 0) sm_text = atomicAdd(next_text, 1ull);
+        __syncthreads();
+        const uint64_t t = sm_text;
+        if (t >= n) break;
+        const float4 *tok = reinterpret_cast<const float4 *>(tokens + t * (uint64_t)seq * hidden);
+        for (uint32_t i = threadIdx.x; i < seq; i += blockDim.x) sm_mask[i] = mask[t * seq + i];
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t cnt = 0;
+            for (uint32_t i0 = 0; i0 < seq; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const float m = i < seq ? sm_mask[i] : 0.0f;
+                const bool keep = i < seq && !(skip_masked && m == 0.0f);
+                const unsigned b = __ballot_sync(FULL, keep);
+                if (keep) {
+                    const uint32_t pos = cnt + __popc(b & ((1u << lane) - 1u));
+                    sm_idx[pos] = i;
+                    sm_mv[pos] = m;
+                }
+                cnt += __popc(b);
+            }
+            if (lane == 0) sm_cnt = cnt;
+        }
+        __syncthreads();
+        const uint32_t cnt = sm_cnt;
+        float mask_sum = 0.0f;
+        for (uint32_t i = 0; i < seq; ++i) mask_sum = __fadd_rn(mask_sum, sm_mask[i]);
+        for (uint32_t j = threadIdx.x; j < h4; j += blockDim.x) {
+            const float4 *col = tok + j;
+            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            uint32_t c = 0;
+            for (; c + 8 <= cnt; c += 8) {
+                float4 e[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) e[u] = __ldg(col + (uint64_t)sm_idx[c + u] * h4);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float m = sm_mv[c + u];
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(e[u].x, m)); acc.y = __fadd_rn(acc.y, __fmul_rn(e[u].y, m));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(e[u].z, m)); acc.w = __fadd_rn(acc.w, __fmul_rn(e[u].w, m));
+                }
+            }
+            for (; c < cnt; ++c) {
+                const float4 e = __ldg(col + (uint64_t)sm_idx[c] * h4);
+                const float m = sm_mv[c];
+                acc.x = __fadd_rn(acc.x, __fmul_rn(e.x, m)); acc.y = __fadd_rn(acc.y, __fmul_rn(e.y, m));
+                acc.z = __fadd_rn(acc.z, __fmul_rn(e.z, m)); acc.w = __fadd_rn(acc.w, __fmul_rn(e.w, m));
+            }
+            if (mask_sum > 0.0f) { acc.x = acc.x / mask_sum; acc.y = acc.y / mask_sum; acc.z = acc.z / mask_sum; acc.w = acc.w / mask_sum; }
+            reinterpret_cast<float4 *>(sm_pool)[j] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float ss = 0.0f;
+#pragma unroll 8
+            for (uint32_t j = 0; j < hidden; ++j) ss = __fadd_rn(ss, __fmul_rn(sm_pool[j], sm_pool[j]));
+            sm_norm = sqrtf(ss);
+        }
+        __syncthreads();
+        const float norm = sm_norm;
+        float *o = out + t * out_ld;
+        for (uint32_t j = threadIdx.x; j < out_ld; j += blockDim.x) {
+            float v = 0.0f;
+            if (j < hidden) {
+                v = sm_pool[j];
+                if (norm > 0.0f) v = v / norm;
+            }
+            o[j] = v;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace sema
