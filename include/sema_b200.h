@@ -126,7 +126,11 @@ int sema_index_compact_keep(sema_index *idx, const uint8_t *keep, uint64_t *new_
 
 /* On-disk cache of the vector column: the raw rows x dim fp32 matrix as stored
  * (already normalised) plus the validity bytes, so a restart re-uploads instead of re-embedding.
- * File: 64-byte header {"SEMAIDX1", dim, metric, n_rows}, n_rows validity bytes, n_rows*dim floats. */
+ * File: 64-byte header {"SEMAIDX1", u32 dim, i32 metric, u64 n_rows, u32 version = 1, u32 byte-order
+ * tag 0x01020304, zero padding}, n_rows validity bytes, n_rows*dim floats (little-endian fp32, dense).
+ * sema_index_load checks the header against the file (version, byte order, field ranges, and
+ * size == 64 + n_rows + n_rows*dim*4) before it allocates anything: a corrupt or truncated file is
+ * SEMA_ERR_INVALID.  Neither call holds more than a 64 k-row staging chunk on the host. */
 int sema_index_save(sema_index *idx, const char *path);
 int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_index **out);
 

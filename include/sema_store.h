@@ -56,7 +56,11 @@ typedef int (*sema_embed_fn)(void *user, const char *text, float *out, uint32_t 
 
 /* StorageManager::new / LanceIndexer::new (src/storage/mod.rs:19-29): normalize != 0 applies
  * the mean_pool normalise tail (src/semantic/embeddings.rs:83-88) to stored rows and queries
- * on the device.  The vector index is growable (sema_index_create_growable): capacity_rows bounds
+ * on the device — the reference's pipeline, where every vector is unit-norm and LanceDB's default
+ * squared-L2 order (lance_indexer.rs:121-126) equals descending cosine; scores are then the cosine.
+ * normalize == 0 stores the caller's vectors as given, whatever their norm: the store then ranks by
+ * the literal squared-L2 `_distance` d like the reference does, and the score it returns is
+ * 1 - d/2 (the cosine again whenever the vectors are unit-norm).  The vector index is growable (sema_index_create_growable): capacity_rows bounds
  * the address space only, 0 = no bound short of the 32-bit row ids — the reference's table has no
  * declared size either. */
 int sema_store_create(int device, uint32_t dim, uint64_t capacity_rows, int normalize, sema_store **out);

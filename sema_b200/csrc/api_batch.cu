@@ -336,6 +336,18 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
 
 namespace sema_impl {
 
+int k3_poison_rows(sema_index *s, const uint64_t *rows_dev, uint64_t n)
+{
+    if (!s->planes || s->planes_rows == 0 || n == 0) return SEMA_OK;
+    const uint64_t work = n * (s->dim / 8);
+    uint64_t blocks = (work + 255) / 256;
+    if (blocks > (uint64_t)s->num_sms * 8) blocks = (uint64_t)s->num_sms * 8;
+    k3::poison_planes_kernel<<<(unsigned)blocks, 256, 0, s->stream>>>(s->planes, s->dim, rows_dev, n, s->planes_rows);
+    CK(cudaGetLastError());
+    s->launches++;
+    return SEMA_OK;
+}
+
 // Batched search with the queries already on the device (nq x dim dense).
 int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
                uint32_t *nf_d)

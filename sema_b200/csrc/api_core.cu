@@ -20,6 +20,7 @@ int fail(int code, const char *fmt, ...)
 
 int poll_ingest(sema_index *s, bool wait)
 {
+    if (s->poisoned) return fail(SEMA_ERR_CUDA, "index unusable: an earlier compaction failed half-way");
     while (!s->pending.empty()) {
         Pending &p = s->pending.front();
         cudaError_t e = wait ? cudaEventSynchronize(p.ev) : cudaEventQuery(p.ev);
@@ -43,25 +44,34 @@ int ensure(void **p, size_t *cap, size_t need)
     return SEMA_OK;
 }
 
+// K1 grid: a warp owns groups of 32 rows; enough blocks to fill the GPU, never more than the groups need
+static unsigned ingest_blocks(const sema_index *s, uint64_t n)
+{
+    const uint64_t groups = (n + 31) / 32;
+    uint64_t blocks = (groups + INGEST_SEQ_WARPS - 1) / INGEST_SEQ_WARPS;
+    const uint64_t maxb = (uint64_t)s->num_sms * 12;
+    if (blocks > maxb) blocks = maxb;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
 // K1 on query vectors in place (nq rows of `stride` floats on the device, on the query stream)
 int normalize_queries_dev(sema_index *s, float *q, uint64_t stride, uint32_t nq)
 {
     for (uint32_t done = 0; done < nq; done += 65536) {
         const uint32_t m = (nq - done) < 65536u ? (nq - done) : 65536u;
-        uint64_t blocks = ((uint64_t)m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
-        if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
         float *base = q + (size_t)done * stride;
-        // src == dst, same stride; pad columns [dim, stride) are rewritten as zeros.  Dense, aligned
-        // queries take the float4 kernel: the same per-lane partial sums as the stored rows and as
-        // the in-register normalisation of the host-query path (k2_scan_tma.cuh), so every path
-        // produces the same normalised query bit for bit.
+        // src == dst, same stride; pad columns [dim, stride) are rewritten as zeros.  The same kernel
+        // (the reference's sequential sum order) normalises stored rows, and the host-query path
+        // repeats that order in K2's registers (k2_scan_tma.cuh), so every path produces the same
+        // normalised query bit for bit.
         const bool vec4 = stride == s->dim && (s->dim & 3u) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+        const unsigned blocks = ingest_blocks(s, m);
         if (vec4)
-            ingest_kernel<true><<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(
+            ingest_kernel<4><<<blocks, INGEST_SEQ_WARPS * 32, 0, s->stream>>>(
                 base, stride, base, (uint32_t)stride, s->dim, m, nullptr, s->qscratch,
                 1, reinterpret_cast<float *>(s->qscratch + 65536));
         else
-            ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(
+            ingest_kernel<1><<<blocks, INGEST_SEQ_WARPS * 32, 0, s->stream>>>(
                 base, stride, base, (uint32_t)stride, s->dim, m, nullptr, s->qscratch,
                 1, reinterpret_cast<float *>(s->qscratch + 65536));
         CK(cudaGetLastError());
@@ -78,16 +88,12 @@ int launch_ingest(sema_index *s, const float *src, uint64_t src_ld, uint64_t fir
                   const uint8_t *valid_in, int normalize, bool vec4)
 {
     float *dst = s->X + first * s->ld;
-    uint64_t warps_needed = n;
-    uint64_t blocks = (warps_needed * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
-    const uint64_t maxb = (uint64_t)s->num_sms * 16;
-    if (blocks > maxb) blocks = maxb;
-    if (blocks < 1) blocks = 1;
+    const unsigned blocks = ingest_blocks(s, n);
     if (vec4)
-        ingest_kernel<true><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
+        ingest_kernel<4><<<blocks, INGEST_SEQ_WARPS * 32, 0, s->ingest_stream>>>(
             src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize, s->max_norm2);
     else
-        ingest_kernel<false><<<(unsigned)blocks, INGEST_THREADS, 0, s->ingest_stream>>>(
+        ingest_kernel<1><<<blocks, INGEST_SEQ_WARPS * 32, 0, s->ingest_stream>>>(
             src, src_ld, dst, s->ld, s->dim, n, valid_in, s->valid + first, normalize, s->max_norm2);
     CK(cudaGetLastError());
     s->launches++;
@@ -109,6 +115,7 @@ int publish(sema_index *s, uint64_t n)
 int check_append(sema_index *s, uint64_t n)
 {
     if (!s) return fail(SEMA_ERR_INVALID, "null index");
+    if (s->poisoned) return fail(SEMA_ERR_CUDA, "index unusable: an earlier compaction failed half-way");
     if (s->n_rows + n > s->capacity)
         return fail(SEMA_ERR_CAPACITY, "append of %llu rows exceeds capacity %llu (size %llu)",
                     (unsigned long long)n, (unsigned long long)s->capacity, (unsigned long long)s->n_rows);
@@ -390,11 +397,11 @@ int sema_index_tombstone(sema_index *s, const uint64_t *rows, uint64_t n)
     tombstone_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, s->tomb_dev, n, s->n_rows, s->valid);
     CK(cudaGetLastError());
     s->launches++;
+    // the bf16 planes of K3 must forget the dead rows too: the same rows are NaN-poisoned in place
+    // (16 bytes per plane and 8 columns), so removing a file never re-tiles the planes behind it
+    rc = k3_poison_rows(s, s->tomb_dev, n);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(s->stream));
-    // the bf16 planes of K3 must forget the dead rows: re-tile from the first one on
-    uint64_t lowest = s->planes_rows;
-    for (uint64_t i = 0; i < n; ++i) if (rows[i] < lowest) lowest = rows[i];
-    s->planes_rows = lowest;
     return SEMA_OK;
 }
 
@@ -409,14 +416,19 @@ int sema_index_compact_keep(sema_index *s, const uint8_t *keep, uint64_t *new_ro
     if (!s) return fail(SEMA_ERR_INVALID, "null index");
     int rc = sema_index_flush(s);
     if (rc) return rc;
+    if (s->poisoned) return fail(SEMA_ERR_CUDA, "index unusable: an earlier compaction failed half-way");
     CK(cudaStreamSynchronize(s->stream));
     const uint64_t n = s->n_rows;
-    std::vector<uint8_t> valid(n ? n : 1);
-    if (n) CK(cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> valid, new_valid;
     std::vector<uint32_t> src;   // src[new] = old, ascending
-    std::vector<uint8_t> new_valid;
-    src.reserve(n);
-    new_valid.reserve(n);
+    try {
+        valid.resize(n ? n : 1);
+        src.reserve(n);
+        new_valid.reserve(n);
+    } catch (const std::exception &) {
+        return fail(SEMA_ERR_NOMEM, "host allocation failed (%llu rows)", (unsigned long long)n);
+    }
+    if (n) CK(cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost));
     for (uint64_t r = 0; r < n; ++r) {
         if (keep ? keep[r] != 0 : valid[r] != 0) {
             new_valid.push_back(valid[r]);
@@ -438,25 +450,42 @@ int sema_index_compact_keep(sema_index *s, const uint8_t *keep, uint64_t *new_ro
     if (e == cudaSuccess) e = cudaMalloc(&src_dev, C * sizeof(uint32_t));
     if (e != cudaSuccess) {
         cudaFree(tmp); cudaFree(src_dev); cudaGetLastError();
-        return fail(SEMA_ERR_NOMEM, "compaction scratch: %s", cudaGetErrorString(e));
+        return fail(SEMA_ERR_NOMEM, "compaction scratch: %s", cudaGetErrorString(e));   // nothing has moved yet
     }
     uint64_t first_moved = 0;
     while (first_moved < live && src[first_moved] == first_moved) ++first_moved;   // untouched prefix
-    for (uint64_t at = first_moved; at < live; at += C) {
+    // From the first chunk on, rows move in place: an error half-way would leave X out of step with the
+    // validity bytes, the row count and the caller's chunk table.  It is reported, the scratch
+    // buffers are released, and the handle refuses further work instead of answering from mixed rows.
+    const char *what = nullptr;
+    for (uint64_t at = first_moved; at < live && e == cudaSuccess; at += C) {
         const uint64_t m = (live - at) < C ? (live - at) : C;
-        CK(cudaMemcpyAsync(src_dev, src.data() + at, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        what = "copying the gather list";
+        e = cudaMemcpyAsync(src_dev, src.data() + at, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream);
+        if (e != cudaSuccess) break;
         uint64_t blocks = (m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
         if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
         gather_rows_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, src_dev, m, tmp);
-        CK(cudaGetLastError());
+        what = "gather kernel";
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
         s->launches++;
-        CK(cudaMemcpyAsync(s->X + at * s->ld, tmp, m * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-        CK(cudaStreamSynchronize(s->stream));   // src_dev / tmp are reused by the next chunk
+        what = "moving a chunk into place";
+        e = cudaMemcpyAsync(s->X + at * s->ld, tmp, m * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);   // src_dev / tmp are reused by the next chunk
     }
-    if (live) CK(cudaMemcpyAsync(s->valid, new_valid.data(), live, cudaMemcpyHostToDevice, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    if (e == cudaSuccess && live) {
+        what = "writing the validity bytes";
+        e = cudaMemcpyAsync(s->valid, new_valid.data(), live, cudaMemcpyHostToDevice, s->stream);
+    }
+    if (e == cudaSuccess) { what = "final synchronise"; e = cudaStreamSynchronize(s->stream); }
     cudaFree(tmp);
     cudaFree(src_dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        s->poisoned = true;
+        return fail(SEMA_ERR_CUDA, "compaction failed while %s: %s; the index is now unusable (destroy and rebuild it)", what,
+                    cudaGetErrorString(e));
+    }
     s->n_rows = live;
     s->n_visible = live;
     if (s->planes_rows > first_moved) s->planes_rows = first_moved;   // K3 planes: re-tile from the first moved row
@@ -464,12 +493,16 @@ int sema_index_compact_keep(sema_index *s, const uint8_t *keep, uint64_t *new_ro
 }
 
 namespace {
+constexpr uint32_t SEMA_FILE_VERSION = 1;
+constexpr uint32_t SEMA_FILE_ENDIAN_TAG = 0x01020304u;   // reads back differently on a machine of the other byte order
 struct SemaFileHeader {
     char magic[8];
     uint32_t dim;
     int32_t metric;
     uint64_t n_rows;
-    unsigned char pad[40];
+    uint32_t version;       // SEMA_FILE_VERSION (0 in files written before the field existed = version 1)
+    uint32_t endian_tag;    // SEMA_FILE_ENDIAN_TAG (0 in those older files)
+    unsigned char pad[32];
 };
 static_assert(sizeof(SemaFileHeader) == 64, "header is 64 bytes");
 }  // namespace
@@ -488,14 +521,19 @@ int sema_index_save(sema_index *s, const char *path)
     h.dim = s->dim;
     h.metric = s->metric;
     h.n_rows = s->n_rows;
+    h.version = SEMA_FILE_VERSION;
+    h.endian_tag = SEMA_FILE_ENDIAN_TAG;
     bool ok = fwrite(&h, sizeof h, 1, f) == 1;
     const uint64_t n = s->n_rows;
-    std::vector<uint8_t> valid(n ? n : 1);
-    if (ok && n) {
-        cudaError_t e = cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost);
-        ok = e == cudaSuccess && fwrite(valid.data(), 1, n, f) == n;
-    }
     const uint64_t C = 1u << 16;
+    uint8_t *vbuf = static_cast<uint8_t *>(malloc(C));     // validity bytes travel in chunks: nothing scales with n_rows
+    ok = ok && vbuf != nullptr;
+    for (uint64_t at = 0; ok && at < n; at += C) {
+        const uint64_t m = (n - at) < C ? (n - at) : C;
+        cudaError_t e = cudaMemcpy(vbuf, s->valid + at, m, cudaMemcpyDeviceToHost);
+        ok = e == cudaSuccess && fwrite(vbuf, 1, m, f) == m;
+    }
+    free(vbuf);
     float *pin = nullptr;
     if (ok && n) ok = cudaHostAlloc(&pin, C * s->dim * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
     for (uint64_t at = 0; ok && at < n; at += C) {
@@ -521,24 +559,54 @@ int sema_index_load(const char *path, int device, uint64_t capacity_rows, sema_i
         fclose(f);
         return fail(SEMA_ERR_INVALID, "%s is not a sema index file", path);
     }
+    // Nothing in the header is trusted before it has been checked against the file itself: a corrupt
+    // or truncated file must come back as an error code, never as an allocation failure thrown
+    // across the C boundary.
+    const uint32_t version = h.version ? h.version : 1;   // files written before the field existed carry 0
+    if (version != SEMA_FILE_VERSION || (h.endian_tag != 0 && h.endian_tag != SEMA_FILE_ENDIAN_TAG)) {
+        fclose(f);
+        return fail(SEMA_ERR_INVALID, "%s: unsupported file version %u or byte order", path, version);
+    }
+    if (h.dim == 0 || h.dim > SEMA_MAX_DIM || (h.metric != SEMA_METRIC_COSINE && h.metric != SEMA_METRIC_L2) ||
+        h.n_rows > 0xfffffffeull) {
+        fclose(f);
+        return fail(SEMA_ERR_INVALID, "%s: corrupt header (dim %u, metric %d, rows %llu)", path, h.dim, h.metric,
+                    (unsigned long long)h.n_rows);
+    }
+    long long fsize = -1;
+    if (fseek(f, 0, SEEK_END) == 0) fsize = ftell(f);
+    const unsigned long long want = 64ull + h.n_rows + h.n_rows * (unsigned long long)h.dim * 4ull;
+    if (fsize < 0 || (unsigned long long)fsize != want || fseek(f, (long)sizeof h, SEEK_SET) != 0) {
+        fclose(f);
+        return fail(SEMA_ERR_INVALID, "%s: size %lld does not match its header (%llu rows x %u: %llu bytes)", path, fsize,
+                    (unsigned long long)h.n_rows, h.dim, want);
+    }
     if (capacity_rows < h.n_rows) capacity_rows = h.n_rows;
     sema_index *s = nullptr;
     int rc = sema_index_create(device, h.dim, capacity_rows, h.metric, &s);
     if (rc) { fclose(f); return rc; }
     const uint64_t n = h.n_rows, C = 1u << 16;
-    std::vector<uint8_t> valid(n ? n : 1);
-    bool ok = n == 0 || fread(valid.data(), 1, n, f) == n;
+    // the validity bytes are read chunk by chunk next to their rows: no allocation scales with n_rows
+    uint8_t *vbuf = static_cast<uint8_t *>(malloc(C));
     float *pin = nullptr;
-    if (ok && n) ok = cudaHostAlloc(&pin, C * h.dim * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+    bool ok = vbuf != nullptr;
+    if (!ok) rc = fail(SEMA_ERR_NOMEM, "host allocation failed");
+    if (ok && n) {
+        ok = cudaHostAlloc(&pin, C * h.dim * sizeof(float), cudaHostAllocDefault) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); rc = fail(SEMA_ERR_NOMEM, "pinned staging buffer"); }
+    }
     for (uint64_t at = 0; ok && at < n; at += C) {
         const uint64_t m = (n - at) < C ? (n - at) : C;
-        ok = fread(pin, sizeof(float), m * h.dim, f) == m * h.dim;
+        ok = fseek(f, (long)(sizeof h + at), SEEK_SET) == 0 && fread(vbuf, 1, m, f) == m &&
+             fseek(f, (long)(sizeof h + n + at * h.dim * sizeof(float)), SEEK_SET) == 0 &&
+             fread(pin, sizeof(float), m * h.dim, f) == m * h.dim;
         if (ok) {
-            rc = sema_index_append(s, pin, m, valid.data() + at, /*normalize=*/0, nullptr);   // rows are stored normalised
+            rc = sema_index_append(s, pin, m, vbuf, /*normalize=*/0, nullptr);   // rows are stored normalised
             ok = rc == SEMA_OK;
         }
     }
     if (pin) cudaFreeHost(pin);
+    free(vbuf);
     fclose(f);
     if (!ok) {
         sema_index_destroy(s);

@@ -104,8 +104,16 @@ Status GpuVectorIndexer::open(int device, uint32_t dim, uint64_t capacity_rows, 
     // space only (0 = as many rows as 32-bit row ids allow); a driver without virtual memory
     // management gets the fixed-capacity index instead
     const uint64_t max_rows = capacity_rows ? capacity_rows : 0xfffffffeull;
-    int rc = sema_index_create_growable(device, dim, max_rows, SEMA_METRIC_COSINE, &idx_);
-    if (rc == SEMA_ERR_UNSUPPORTED && capacity_rows) rc = sema_index_create(device, dim, capacity_rows, SEMA_METRIC_COSINE, &idx_);
+    // Ranking metric.  The reference ranks by LanceDB's default squared-L2 `_distance`
+    // (lance_indexer.rs:121-126 sets no distance_type).  With normalize (the reference's own
+    // pipeline: every row and query passes through the mean_pool normalise tail) all vectors are
+    // unit-norm, L2^2 = 2 - 2 cos, and the dot-product kernel gives the same order and the cosine
+    // directly.  Without it the caller's vectors may have any norm, where only the literal L2
+    // metric ranks like the reference: the index is then created with SEMA_METRIC_L2 and the
+    // score handed out is 1 - d/2 (= the cosine whenever the vectors do happen to be unit-norm).
+    metric_ = normalize ? SEMA_METRIC_COSINE : SEMA_METRIC_L2;
+    int rc = sema_index_create_growable(device, dim, max_rows, metric_, &idx_);
+    if (rc == SEMA_ERR_UNSUPPORTED && capacity_rows) rc = sema_index_create(device, dim, capacity_rows, metric_, &idx_);
     if (rc) return from_rc(rc);
     dim_ = dim;
     normalize_ = normalize;
@@ -159,7 +167,9 @@ Status GpuVectorIndexer::search(const float *q, size_t limit, std::vector<std::p
     for (uint32_t i = 0; i < nf; ++i) {  // lance_indexer.rs:131-138: rows -> Chunk, in rank order
         const uint64_t row = ids_buf_[i];
         if (row >= chunks_.size()) return Status::Err(SEMA_ERR_INVALID, "GPU returned a row outside the chunk table");
-        out->emplace_back(chunks_[row], sc_buf_[i]);  // the real score (mod.rs:123 attaches 1.0)
+        // the real score (mod.rs:123 attaches 1.0): the cosine, or 1 - d/2 under the literal L2 metric
+        const float score = metric_ == SEMA_METRIC_L2 ? 1.0f - 0.5f * sc_buf_[i] : sc_buf_[i];
+        out->emplace_back(chunks_[row], score);
         if (rows) rows->push_back(row);
     }
     return Status::Ok();

@@ -100,6 +100,7 @@ private:
     sema_index *idx_ = nullptr;
     uint32_t dim_ = 0;
     bool normalize_ = false;
+    int metric_ = SEMA_METRIC_COSINE;   // SEMA_METRIC_L2 when the caller's vectors are stored as given (normalize = false)
     std::vector<Chunk> chunks_;   // row -> Chunk (extract_chunk_from_batch, :252-281)
     std::vector<uint8_t> live_;   // 0 after remove_file_chunks
     std::vector<uint64_t> ids_buf_;

@@ -11,9 +11,11 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <deque>
+#include <exception>
 #include <new>
 #include <vector>
 
@@ -107,6 +109,7 @@ struct sema_index {
     unsigned char *planes = nullptr;    // pre-tiled bf16 hi/lo planes, built lazily
     uint64_t planes_rows = 0;           // rows [0, planes_rows) are reflected in the planes
     bool planes_failed = false;         // allocation failed once: stay on the K2 loop
+    bool poisoned = false;              // a compaction failed after rows had started to move: every later call is refused
     float *Qpad_dev = nullptr;
     uint32_t *cand_rows = nullptr;
     float *cand_thr = nullptr;
@@ -164,6 +167,8 @@ int staged_query_run(sema_index *s, const float *q_host, uint32_t n, uint32_t k,
 // ticket bookkeeping shared by the index-level and the shard-group submit / collect entry points
 int slot_claim(sema_index *s, uint32_t k, uint64_t *ticket);                    // next ticket; fails when its slot is still uncollected
 int slot_collect(sema_index *s, uint64_t ticket, uint64_t *row_ids, float *scores, uint32_t *n_found);
+// api_batch.cu: NaN-poison the listed local rows (device array, on the query stream) in K3's bf16 planes; no-op without planes
+int k3_poison_rows(sema_index *s, const uint64_t *rows_dev, uint64_t n);
 // api_batch.cu: nq device-resident queries (nq x dim dense); K3 when the shape allows, else K2 per query
 int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
                uint32_t *nf_d);

@@ -6,8 +6,8 @@
 // column of src/storage/lance_indexer.rs:41-45, 66-76: a null row (valid == 0), or
 // a row holding a non-finite value, is stored as quiet NaNs so that K2's
 // `score == score` test drops it without reading a validity bitmap.
-// One warp per row; IEEE sqrt and divide (no fast-math), so the only difference
-// from the reference's sequential sum is the summation order (<= a few ulp).
+// IEEE multiply, add, sqrt and divide in the reference's own order (no FMA, no
+// fast-math, no re-association): the stored rows are bit-identical to the reference's.
 #pragma once
 #include <float.h>
 #include "common.cuh"
@@ -42,64 +42,119 @@ synth_kernel(float *dst, uint32_t ld, uint32_t d, uint64_t seed, uint64_t row0, 
     }
 }
 
-// src: n rows, stride src_ld floats (may alias dst).  dst: stride ld floats, columns
-// [d, ld) are zero padding.  valid_in nullable.  valid_out: one byte per row.
-template <bool VEC4>
-__global__ void __launch_bounds__(INGEST_THREADS)
+// src: n rows, stride src_ld floats (may alias dst when the strides agree).  dst: stride ld floats,
+// columns [d, ld) are zero padding.  valid_in nullable (may alias valid_out).  valid_out: one byte per row.
+//
+// The squared norm is summed in the REFERENCE'S ORDER — `pooled.iter().map(|x| x * x).sum::<f32>()`
+// (src/semantic/embeddings.rs:84) is a sequential f32 fold over j = 0, 1, ..., d-1, multiply then add —
+// so the stored rows are bit-identical to the reference's (and to oracle/cpu_scan.c:sema_oracle_normalize),
+// not merely within a few ulp.  A sequential sum cannot be split over lanes, so the work is transposed:
+// a warp owns 32 consecutive rows; it stages a [32 rows] x [CH columns] tile of them in shared memory
+// with coalesced loads (every warp-level load covers one row's contiguous 128 / 512 bytes), then lane r
+// folds row r's CH values in order (conflict-free: row stride CH + VW words).  The second pass re-reads
+// the rows (L2 hits: the warp has just streamed them), scales and writes them.  HBM traffic stays one
+// read + one write per row; ingest from the host is PCIe-bound long before this kernel matters.
+// VW = 4: float4 accesses (d % 4 == 0, src_ld % 4 == 0, 16-byte aligned src); VW = 1: any shape.
+constexpr int INGEST_SEQ_WARPS = 2;          // 2 x 16.9 KB tiles: static shared memory, up to 6 blocks per SM
+template <int VW> struct IngestTile {
+    static constexpr int CH = 32 * VW;          // columns per staged chunk
+    static constexpr int STRIDE = CH + VW;      // words per tile row: LDS.128 / LDS.32 by row are conflict-free
+    static constexpr int WORDS = 32 * STRIDE;
+};
+
+template <int VW>
+__global__ void __launch_bounds__(INGEST_SEQ_WARPS * 32)
 ingest_kernel(const float *src, uint64_t src_ld, float *dst, uint32_t ld, uint32_t d, uint64_t n,
               const uint8_t *valid_in, uint8_t *valid_out, int normalize, float *max_norm2)
 {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    using T = IngestTile<VW>;
+    __shared__ __align__(16) float tiles[INGEST_SEQ_WARPS][T::WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *tile = tiles[warp];
+    const uint64_t gw = (uint64_t)blockIdx.x * INGEST_SEQ_WARPS + warp;
+    const uint64_t nw = (uint64_t)gridDim.x * INGEST_SEQ_WARPS;
+    const uint64_t groups = (n + 31) / 32;
     const float qnan = __uint_as_float(0x7fc00000u);
 
-    for (uint64_t r = warp0; r < n; r += nwarps) {
-        const float *s = src + r * src_ld;
-        float *o = dst + r * (uint64_t)ld;
-        float ss = 0.0f;
-        if (VEC4) {
-            for (uint32_t j = lane; j < d / 4; j += 32) {
-                const float4 v = reinterpret_cast<const float4 *>(s)[j];
-                ss = __fadd_rn(ss, __fmul_rn(v.x, v.x)); ss = __fadd_rn(ss, __fmul_rn(v.y, v.y));
-                ss = __fadd_rn(ss, __fmul_rn(v.z, v.z)); ss = __fadd_rn(ss, __fmul_rn(v.w, v.w));
-            }
-        } else {
-            for (uint32_t j = lane; j < d; j += 32) {
-                const float v = s[j];
-                ss = __fadd_rn(ss, __fmul_rn(v, v));  // x*x then add, as the reference (no FMA)
-            }
-        }
+    for (uint64_t g = gw; g < groups; g += nw) {
+        const uint64_t r0 = g * 32;
+        const uint32_t rows = (uint32_t)((n - r0) < 32 ? (n - r0) : 32);
+        float ss = 0.0f;                                   // lane r: running sum of row r0 + r
+        for (uint32_t c0 = 0; c0 < d; c0 += T::CH) {
+            // ---- stage rows [r0, r0+rows) x columns [c0, c0+CH): 16 row loads in flight per lane
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL, ss, m);
-
-        bool ok = ss <= FLT_MAX;  // false for NaN / inf anywhere in the row
-        if (valid_in && valid_in[r] == 0) ok = false;  // may alias valid_out[r]: read by all lanes first
+            for (int half = 0; half < 2; ++half) {
+                if (VW == 4) {
+                    float4 v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t rr = half * 16 + i, c = c0 + lane * 4;
+                        v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        if (rr < rows && c < d) v[i] = *reinterpret_cast<const float4 *>(src + (r0 + rr) * src_ld + c);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        *reinterpret_cast<float4 *>(tile + (half * 16 + i) * T::STRIDE + lane * 4) = v[i];
+                } else {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t rr = half * 16 + i, c = c0 + lane;
+                        v[i] = (rr < rows && c < d) ? src[(r0 + rr) * src_ld + c] : 0.0f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) tile[(half * 16 + i) * T::STRIDE + lane] = v[i];
+                }
+            }
+            __syncwarp();
+            // ---- lane r folds its row's values in column order: ss = ss + x*x (no FMA), as the reference
+            const uint32_t jn = (d - c0) < (uint32_t)T::CH ? (d - c0) : (uint32_t)T::CH;
+            const float *mine = tile + lane * T::STRIDE;
+            if (VW == 4) {
+                for (uint32_t j = 0; j < jn; j += 4) {     // d % 4 == 0
+                    const float4 x = *reinterpret_cast<const float4 *>(mine + j);
+                    ss = __fadd_rn(ss, __fmul_rn(x.x, x.x)); ss = __fadd_rn(ss, __fmul_rn(x.y, x.y));
+                    ss = __fadd_rn(ss, __fmul_rn(x.z, x.z)); ss = __fadd_rn(ss, __fmul_rn(x.w, x.w));
+                }
+            } else {
+                for (uint32_t j = 0; j < jn; ++j) ss = __fadd_rn(ss, __fmul_rn(mine[j], mine[j]));
+            }
+            __syncwarp();
+        }
+        // ---- per-row outcome (lane r <-> row r0 + r)
+        bool ok = ss <= FLT_MAX;                           // false for NaN / inf anywhere in the row
+        if ((uint32_t)lane < rows && valid_in && valid_in[r0 + lane] == 0) ok = false;
         const float norm = sqrtf(ss);
         const bool scale = normalize && norm > 0.0f;
-
-        if (VEC4) {
-            for (uint32_t j = lane; j < ld / 4; j += 32) {
-                float4 v = reinterpret_cast<const float4 *>(s)[j];
-                if (!ok) v = make_float4(qnan, qnan, qnan, qnan);
-                else if (scale) { v.x = v.x / norm; v.y = v.y / norm; v.z = v.z / norm; v.w = v.w / norm; }
-                reinterpret_cast<float4 *>(o)[j] = v;
-            }
-        } else {
-            // dst may alias src with a different stride only when ld == src_ld; all
-            // reads of this row happened above or happen before the write of the same j
-            for (uint32_t j = lane; j < ld; j += 32) {
-                float v = j < d ? s[j] : 0.0f;
-                if (j < d) {
-                    if (!ok) v = qnan;
-                    else if (scale) v = v / norm;
+        // ---- second pass: scale and write, one row at a time, coalesced
+        for (uint32_t rr = 0; rr < rows; ++rr) {
+            const float nrm = __shfl_sync(FULL, norm, rr);
+            const bool okr = __shfl_sync(FULL, (int)ok, rr) != 0, scr = __shfl_sync(FULL, (int)scale, rr) != 0;
+            const float *s = src + (r0 + rr) * src_ld;
+            float *o = dst + (r0 + rr) * (uint64_t)ld;
+            if (VW == 4) {
+                for (uint32_t j = lane; j < ld / 4; j += 32) {
+                    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (j * 4 < d) v = reinterpret_cast<const float4 *>(s)[j];
+                    if (j * 4 < d) {
+                        if (!okr) v = make_float4(qnan, qnan, qnan, qnan);
+                        else if (scr) { v.x = v.x / nrm; v.y = v.y / nrm; v.z = v.z / nrm; v.w = v.w / nrm; }
+                    }
+                    reinterpret_cast<float4 *>(o)[j] = v;
                 }
-                o[j] = v;
+            } else {
+                for (uint32_t j = lane; j < ld; j += 32) {
+                    float v = j < d ? s[j] : 0.0f;
+                    if (j < d) {
+                        if (!okr) v = qnan;
+                        else if (scr) v = v / nrm;
+                    }
+                    o[j] = v;
+                }
             }
         }
-        __syncwarp();
-        if (lane == 0) {
-            valid_out[r] = ok ? 1 : 0;
+        if ((uint32_t)lane < rows) {
+            valid_out[r0 + lane] = ok ? 1 : 0;
             // non-negative floats order like unsigned ints; K3 uses max_norm2[0] = max |x|^2 to bound its
             // error and max_norm2[1] = min |x|^2 (L2 metric: how far the dot product is from the distance)
             if (ok) {
@@ -107,6 +162,7 @@ ingest_kernel(const float *src, uint64_t src_ld, float *dst, uint32_t ld, uint32
                 atomicMin(reinterpret_cast<unsigned int *>(max_norm2) + 1, __float_as_uint(scale ? 0.9999995f : ss));
             }
         }
+        __syncwarp();
     }
 }
 

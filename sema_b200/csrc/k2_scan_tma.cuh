@@ -122,16 +122,17 @@ scan_topk_tma_kernel(const __grid_constant__ ScanParams p, const __grid_constant
         }
         if constexpr (QP) {
             if (p.normalize_query) {
-                // K1's rule and order: lane l sums its float4 l, l+32, ... element by element (multiply,
-                // then add), butterfly over the lanes; a non-finite query becomes NaN (never matches)
+                // K1's rule and order, which is the reference's (src/semantic/embeddings.rs:84): a sequential
+                // fold over j = 0 .. dim-1, multiply then add.  The query sits in the kernel parameters
+                // (constant bank, uniform reads), so every thread simply walks it in order — ~1 us, hidden
+                // behind the first TMA round trip; a non-finite query becomes NaN (never matches)
                 float ss = 0.0f;
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    ss = __fadd_rn(ss, __fmul_rn(qv[v].x, qv[v].x)); ss = __fadd_rn(ss, __fmul_rn(qv[v].y, qv[v].y));
-                    ss = __fadd_rn(ss, __fmul_rn(qv[v].z, qv[v].z)); ss = __fadd_rn(ss, __fmul_rn(qv[v].w, qv[v].w));
+#pragma unroll 4
+                for (int j = 0; j < NV * 32; ++j) {
+                    const float4 x = qa.v[j];
+                    ss = __fadd_rn(ss, __fmul_rn(x.x, x.x)); ss = __fadd_rn(ss, __fmul_rn(x.y, x.y));
+                    ss = __fadd_rn(ss, __fmul_rn(x.z, x.z)); ss = __fadd_rn(ss, __fmul_rn(x.w, x.w));
                 }
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(FULL, ss, m);
                 const bool ok = ss <= 3.402823466e+38f;
                 const float norm = sqrtf(ss), qnan = __uint_as_float(0x7fc00000u);
 #pragma unroll

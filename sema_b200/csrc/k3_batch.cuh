@@ -208,6 +208,27 @@ split_planes_kernel(const float *X, uint32_t ld, uint32_t dim, uint64_t row_begi
     }
 }
 
+// Tombstones (sema_index_tombstone): the listed local rows become NaN in both planes, in place — the
+// same addresses split_planes_kernel writes for them — so deleting a file's chunks costs 2 x 16 bytes
+// per row and 8 columns instead of a re-tiling of everything behind the first dead row.  A NaN score
+// never passes the epilogue's `score > threshold`, exactly like a NaN row of X in K2.
+__global__ void __launch_bounds__(256)
+poison_planes_kernel(unsigned char *planes, uint32_t dim, const uint64_t *rows, uint64_t n, uint64_t planes_rows)
+{
+    const uint32_t chunks = dim / 8;
+    const uint64_t total = n * chunks;
+    const uint4 nan8 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);   // 8 x bf16 quiet NaN
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = rows[i / chunks];
+        if (row >= planes_rows) continue;              // not tiled yet: split_planes_kernel will read the NaN row of X
+        const uint32_t c = (uint32_t)(i % chunks), r = (uint32_t)(row % TILE_N);
+        unsigned char *base = planes + (row / TILE_N) * tile_bytes((int)dim) + (size_t)(c / 8) * STAGE_BYTES +
+                              (size_t)(c % 8) * (TILE_N * 16) + (size_t)(r / 8) * 128 + (size_t)(r % 8) * 16;
+        *reinterpret_cast<uint4 *>(base) = nan8;
+        *reinterpret_cast<uint4 *>(base + STAGE_PLANE_BYTES) = nan8;
+    }
+}
+
 // ---------------------------------------------------------------- the batched scan
 struct Params {
     const unsigned char *planes;  // pre-tiled hi/lo planes

@@ -47,8 +47,26 @@ def test_k1_normalize_matches_reference_rule(sema, d):
     assert np.array_equal(got[3], np.zeros(d, np.float32))     # zero row stays zero
     if d >= 2:
         assert np.array_equal(got[4, :2], np.array([3.0, 4.0], np.float32) / np.float32(5.0))
-    # only the summation order differs from the sequential reference sum
-    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-9)
+    # K1 folds the squares in the reference's sequential order (multiply, then add; IEEE sqrt and divide):
+    # the stored rows are the reference's bits, not merely close to them
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,d", [(1, 384), (31, 384), (33, 384), (4099, 384), (1000, 768), (129, 1024), (77, 132), (65, 7)])
+def test_k1_is_bit_identical_to_the_sequential_reference_sum(sema, oracle_c, n, d):
+    # src/semantic/embeddings.rs:83-88 — ragged row counts (warps own groups of 32 rows), chunked columns,
+    # large dynamic range inside a row (the fold order matters most there), host / device / query entry points
+    rng = np.random.default_rng(n * 1000 + d)
+    raw = (rng.standard_normal((n, d)) * np.exp(rng.uniform(-12, 12, (n, d)))).astype(np.float32)
+    want = oracle_c.normalize(raw)
+    assert np.array_equal(want, O.normalize(raw))              # C and NumPy restatements agree
+    with sema.GpuIndex(d, 2 * n + 8) as idx:
+        idx.append(raw, normalize=True)
+        assert np.array_equal(idx.read_rows(0, n), want)
+        import torch
+        dev_rows = torch.from_numpy(raw).cuda()
+        idx.append_device(dev_rows.data_ptr(), n, None, normalize=True)
+        assert np.array_equal(idx.read_rows(n, n), want)
 
 
 def test_k1_no_normalize_is_bit_exact_copy(sema):
@@ -450,14 +468,21 @@ def test_k3_null_rows_appends_and_tombstones(sema, oracle_c):
             O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
         # ... and tombstones
         dead = np.unique(ids[:, 0])
+        l0 = idx.launch_count
+        ids, sc, nf = idx.search_batch(Q, k)
+        per_batch = idx.launch_count - l0                   # kernels of one batch on up-to-date planes
         idx.tombstone(dead)
         v2 = valid.copy()
         v2[dead.astype(np.int64)] = 0
+        l0 = idx.launch_count
         ids, sc, nf = idx.search_batch(Q, k)
+        # the dead rows were NaN-poisoned inside the planes: no re-tiling (split_planes launch) follows a tombstone
+        assert idx.launch_count - l0 == per_batch
         r = oracle_c.scan_batch(np.nan_to_num(X), Q, k, valid=v2)
         for i in range(32):
             O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
-        assert idx.batch_stats()[0] == 96
+        assert not np.isin(ids, dead).any()
+        assert idx.batch_stats()[0] == 128
 
 
 def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
@@ -583,6 +608,33 @@ def test_save_and_load_round_trip(sema, oracle_c, tmp_path):
         idx2.close()
     with pytest.raises(sema.SemaError):
         sema.GpuIndex.load(str(tmp_path / "missing.semaidx"))
+    # a damaged file is an error code, never an allocation failure thrown across the C boundary:
+    blob = open(path, "rb").read()
+    cases = {
+        "truncated": blob[:len(blob) - 1000],
+        "trailing": blob + b"\0" * 8,
+        "huge_rows": blob[:16] + (2 ** 40).to_bytes(8, "little") + blob[24:],     # n_rows far beyond the file
+        "rows_over_32bit_ids": blob[:16] + (2 ** 33).to_bytes(8, "little") + blob[24:],
+        "zero_dim": blob[:8] + (0).to_bytes(4, "little") + blob[12:],
+        "bad_metric": blob[:12] + (7).to_bytes(4, "little") + blob[16:],
+        "future_version": blob[:24] + (99).to_bytes(4, "little") + blob[28:],
+        "header_only_half": blob[:30],
+    }
+    for name, data in cases.items():
+        bad = str(tmp_path / f"{name}.semaidx")
+        open(bad, "wb").write(data)
+        with pytest.raises(sema.SemaError) as ei:
+            sema.GpuIndex.load(bad)
+        assert ei.value.code == -1, name                                    # SEMA_ERR_INVALID
+    # files written before the version / byte-order fields existed (both zero) still load
+    old = str(tmp_path / "v0.semaidx")
+    open(old, "wb").write(blob[:24] + b"\0" * 8 + blob[32:])
+    idx3 = sema.GpuIndex.load(old)
+    try:
+        got = idx3.search(q, k)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    finally:
+        idx3.close()
 
 
 def test_arrow_fixed_size_list_import(sema, oracle_c):

@@ -149,3 +149,28 @@ def test_store_compaction_keeps_null_chunks_and_drops_removed_files():
         assert got[0][0].id == "f0.md:3"
         assert sorted(c.id for c, _ in got) == ["f0.md:0", "f0.md:3", "f0.md:6", "f2.md:2"]   # the null chunk never matches
         assert [c.id for c, _ in m.search("???", 10)] == ["f2.md:5"]                           # ... but LIKE still finds it
+
+
+def test_store_without_normalisation_ranks_by_l2_like_the_reference(oracle_c):
+    """normalize=False stores the caller's vectors as given.  The reference ranks by LanceDB's default
+    squared-L2 `_distance` (src/storage/lance_indexer.rs:121-126), which differs from the dot-product
+    order as soon as the norms differ: the store must follow the L2 order (and hand out 1 - d/2)."""
+    from sema_b200.storage import Chunk, StorageManager
+    rng = np.random.default_rng(11)
+    n, d, k = 4000, corpus.DIM, 10
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X *= rng.uniform(0.2, 5.0, (n, 1)).astype(np.float32)                  # norms all over the place
+    X[7] = 0.0                                                              # a zero-padded / zero vector
+    chunks = [Chunk(f"f{i % 37}.md:{i}", f"f{i % 37}.md", i + 1, i + 2, f"chunk {i}") for i in range(n)]
+    q = rng.standard_normal(d).astype(np.float32)
+    with StorageManager(dim=d, capacity_rows=n + 8, normalize=False, embedder=lambda t: q) as mgr:
+        mgr.index_chunks(chunks, vectors=X)
+        got = mgr.search_vector(q, k)
+        via_text = mgr.search("anything", k)
+    l2_ids, l2_d = oracle_c.scan(X, q, k, metric=oracle_c.METRIC_L2)
+    dot_ids, _ = oracle_c.scan(X, q, k, metric=oracle_c.METRIC_DOT)
+    assert not np.array_equal(l2_ids, dot_ids)                              # the two metrics really disagree here
+    got_rows = np.array([int(c.id.split(":")[1]) for c, _ in got], dtype=np.uint64)
+    assert np.array_equal(got_rows, l2_ids)                                 # gaps between distances are >> 1e-5 here
+    np.testing.assert_allclose([s for _, s in got], 1.0 - 0.5 * l2_d, rtol=1e-5, atol=1e-5)
+    assert [c.id for c, _ in via_text] == [c.id for c, _ in got]
