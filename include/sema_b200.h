@@ -167,7 +167,11 @@ int sema_index_search_collect(sema_index *idx, uint64_t ticket, uint64_t *row_id
  * Results are identical either way. */
 int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32_t k,
                             uint64_t *row_ids, float *scores, uint32_t *n_found);
-/* Same with queries and results resident on the device (Q_dev: nq x dim dense). */
+/* Same with queries and results resident on the device (Q_dev: nq x dim dense): no host copies of
+ * queries or results.  The call still SYNCHRONISES the query stream once per tensor-core stage: each
+ * stage ends with a per-query exactness flag that the host reads back (4 bytes per query) to decide
+ * which queries go on to the next stage of the cascade / to K2.  On return the work of the last
+ * stage may still be running on the query stream; results are ordered after it on that stream. */
 int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
 /* A query stream: nq independent single-query searches (kernel K2 once per query, one HBM pass
@@ -234,6 +238,18 @@ typedef struct sema_shard_group sema_shard_group;
 #define SEMA_IPC_HANDLE_BYTES 64
 #define SEMA_MAX_SHARDS 16
 int sema_shard_group_create(sema_index *idx, uint32_t world, uint32_t rank, sema_shard_group **out);
+/* Single-process form — what a drop-in for the reference needs: Sema is ONE process that owns ONE
+ * StorageManager (src/main.rs:9, src/storage/mod.rs:13-16, src/tui/engine.rs:30), so all the GPUs of
+ * the box have to hang off one handle.  shards[r] is an index created on its own device (one shard
+ * per GPU; set each shard's sema_index_set_row_base so that ids are global; ingest into the shards
+ * with the ordinary append calls).  Peer access between the devices replaces the IPC handles, so
+ * there is no handle exchange and no connect step.  sema_shard_group_search / _submit / _collect on
+ * such a group take ONE host call: a worker thread per shard launches that shard's fused scan +
+ * exchange + merge kernel (all N launches leave the host together), every GPU ends up with the
+ * global top-k and the call returns shard 0's copy.  While the group exists, search its shards only
+ * through the group.  The device-resident variants (_search_device, _search_stream_device) return
+ * SEMA_ERR_UNSUPPORTED on a local group: a device-resident query lives on one GPU. */
+int sema_shard_group_create_local(sema_index *const *shards, uint32_t n_shards, sema_shard_group **out);
 int sema_shard_group_local_handle(sema_shard_group *g, void *handle_out /* 64 bytes */);
 int sema_shard_group_connect(sema_shard_group *g, const void *handles /* world x 64 bytes, by rank */);
 int sema_shard_group_search(sema_shard_group *g, const float *q, uint32_t k, uint64_t *row_ids,
@@ -253,7 +269,12 @@ int sema_shard_group_search_stream_device(sema_shard_group *g, const float *Q_de
 int sema_shard_group_destroy(sema_shard_group *g);
 
 /* ---- properties ------------------------------------------------------------ */
-int sema_index_set_row_base(sema_index *idx, uint64_t row_base); /* shard offset of row 0   */
+/* Shard offset of row 0.  HARD LIMIT: global row ids are 32-bit inside the ranking keys the kernels
+ * exchange (key = ordered score << 32 | ~id), so row_base + capacity must stay below 2^32 - 1
+ * (4.29 billion rows per logical index; a 100M-row corpus uses 2 % of it); a row_base that would let
+ * an id reach 2^32 - 1 is refused with SEMA_ERR_INVALID here, and an append that would do so with
+ * SEMA_ERR_CAPACITY.  The uint64_t types at this boundary are the reference-facing width only. */
+int sema_index_set_row_base(sema_index *idx, uint64_t row_base);
 /* external != 0: run searches on the caller's cudaStream_t `cuda_stream` (0 = the CUDA
  * default stream); external == 0: back to the handle's own non-blocking query stream. */
 int sema_index_set_stream(sema_index *idx, void *cuda_stream, int external);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sema_index_search_batch_keys_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp]),
     "sema_topk_merge_batch_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_shard_group_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "sema_shard_group_create_local": (C.c_int, [C.POINTER(_vp), C.c_uint32, C.POINTER(_vp)]),
     "sema_shard_group_local_handle": (C.c_int, [_vp, _vp]),
     "sema_shard_group_connect": (C.c_int, [_vp, _vp]),
     "sema_shard_group_search": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _u32p]),

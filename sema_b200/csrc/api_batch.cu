@@ -307,19 +307,28 @@ int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
             if (rc) return rc;
             rc = ensure(reinterpret_cast<void **>(&s->sub_nf), &s->sub_nf_cap, (size_t)nsub * sizeof(uint32_t));
             if (rc) return rc;
-            for (uint32_t j = 0; j < nsub; ++j)
-                CK(cudaMemcpyAsync(s->sub_q + (size_t)j * s->dim, Qd + (size_t)open_q[j] * s->dim, s->dim * sizeof(float),
-                                   cudaMemcpyDeviceToDevice, s->stream));
+            // one list upload + one gather kernel (was: a small device-to-device copy per query)
+            rc = ensure(reinterpret_cast<void **>(&s->sub_idx), &s->sub_idx_cap, (size_t)nsub * sizeof(uint32_t));
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(s->sub_idx, open_q.data(), (size_t)nsub * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+            {
+                const uint64_t work = (uint64_t)nsub * (s->dim / 4);
+                const unsigned blocks = (unsigned)((work + 255) / 256 < 1024 ? (work + 255) / 256 : 1024);
+                k3::gather_queries_kernel<<<blocks, 256, 0, s->stream>>>(reinterpret_cast<const float4 *>(Qd), s->sub_idx, nsub,
+                                                                         s->dim / 4, reinterpret_cast<float4 *>(s->sub_q));
+                CK(cudaGetLastError());
+                s->launches++;
+            }
             rc = k3_stage(s, s->sub_q, nsub, n, k, 3, s->sub_ids, s->sub_sc, s->sub_nf);
             if (rc) return rc;
+            // proven sub-batch results go back to their places in one kernel (flags_dev holds the sub-batch's flags)
+            k3::scatter_results_kernel<<<nsub, 128, 0, s->stream>>>(s->sub_ids, s->sub_sc, s->sub_nf, s->sub_idx, s->flags_dev, k,
+                                                                    ids_d, sc_d, nf_d);
+            CK(cudaGetLastError());
+            s->launches++;
             std::vector<uint32_t> still;
-            for (uint32_t j = 0; j < nsub; ++j) {
-                const uint32_t i = open_q[j];
-                if (s->flags_pin[j]) { still.push_back(i); continue; }
-                CK(cudaMemcpyAsync(ids_d + (size_t)i * k, s->sub_ids + (size_t)j * k, k * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s->stream));
-                CK(cudaMemcpyAsync(sc_d + (size_t)i * k, s->sub_sc + (size_t)j * k, k * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
-                CK(cudaMemcpyAsync(nf_d + i, s->sub_nf + j, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->stream));
-            }
+            for (uint32_t j = 0; j < nsub; ++j)
+                if (s->flags_pin[j]) still.push_back(open_q[j]);
             open_q.swap(still);
         }
     }

@@ -266,7 +266,7 @@ int sema_index_destroy(sema_index *s)
     cudaFreeHost(s->res_pin); cudaFreeHost(s->res_map); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
     cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
     cudaFree(s->qscratch); cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
-    cudaFree(s->q_aligned); cudaFree(s->sub_q); cudaFree(s->sub_ids); cudaFree(s->sub_sc); cudaFree(s->sub_nf);
+    cudaFree(s->q_aligned); cudaFree(s->sub_q); cudaFree(s->sub_ids); cudaFree(s->sub_sc); cudaFree(s->sub_nf); cudaFree(s->sub_idx);
     cudaFree(s->cand_thr); cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->ingest_stream) cudaStreamDestroy(s->ingest_stream);

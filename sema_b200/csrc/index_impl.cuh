@@ -129,6 +129,8 @@ struct sema_index {
     float *sub_sc = nullptr;
     uint32_t *sub_nf = nullptr;
     size_t sub_q_cap = 0, sub_ids_cap = 0, sub_sc_cap = 0, sub_nf_cap = 0;
+    uint32_t *sub_idx = nullptr;        // cascade: batch positions of those queries
+    size_t sub_idx_cap = 0;
     float *q_aligned = nullptr;         // 16-byte aligned copy of caller queries that are not
     size_t q_aligned_cap = 0;
 };

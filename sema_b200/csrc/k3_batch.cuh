@@ -612,5 +612,31 @@ rescore_kernel(const RescoreParams p)
     }
 }
 
+// ---------------------------------------------------------------- cascade plumbing
+// dst[j] = Q[idx[j]] (rows of dim4 float4): the queries the single-pass stage could not prove, made dense
+__global__ void __launch_bounds__(256)
+gather_queries_kernel(const float4 *Q, const uint32_t *idx, uint32_t nsub, uint32_t dim4, float4 *dst)
+{
+    const uint64_t total = (uint64_t)nsub * dim4;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(i / dim4), c = (uint32_t)(i - (uint64_t)j * dim4);
+        dst[i] = Q[(size_t)idx[j] * dim4 + c];
+    }
+}
+// block j: if the sub-batch proved query j (flags[j] == 0), its k results replace those of query idx[j]
+__global__ void __launch_bounds__(128)
+scatter_results_kernel(const uint64_t *sub_ids, const float *sub_sc, const uint32_t *sub_nf, const uint32_t *idx,
+                       const uint32_t *flags, uint32_t k, uint64_t *ids, float *sc, uint32_t *nf)
+{
+    const uint32_t j = blockIdx.x;
+    if (flags[j] != 0) return;
+    const uint32_t q = idx[j];
+    for (uint32_t e = threadIdx.x; e < k; e += blockDim.x) {
+        ids[(size_t)q * k + e] = sub_ids[(size_t)j * k + e];
+        sc[(size_t)q * k + e] = sub_sc[(size_t)j * k + e];
+    }
+    if (threadIdx.x == 0) nf[q] = sub_nf[j];
+}
+
 }  // namespace k3
 }  // namespace sema

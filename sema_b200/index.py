@@ -326,6 +326,19 @@ class ShardGroup:
             buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
             check(self._L.sema_shard_group_connect(self._g, buf))
 
+    @classmethod
+    def local(cls, shards) -> "ShardGroup":
+        """Single-process group over per-GPU shards (``sema_shard_group_create_local``): one handle, one
+        host call per search, the N fused kernels launched together by the library's worker threads."""
+        self = cls.__new__(cls)
+        self._L = _lib.lib()
+        self.index, self.world, self.rank = shards[0], len(shards), 0
+        self.shards = list(shards)                       # keep the shard handles alive
+        arr = (C.c_void_p * len(shards))(*[s.handle for s in shards])
+        self._g = C.c_void_p()
+        check(self._L.sema_shard_group_create_local(arr, len(shards), C.byref(self._g)))
+        return self
+
     def close(self) -> None:
         if getattr(self, "_g", None) is not None and self._g.value:
             self._L.sema_shard_group_destroy(self._g)

@@ -553,6 +553,84 @@ def test_shard_group_world1_equals_plain_search(sema, oracle_c):
             g.close()
 
 
+@pytest.mark.parametrize("d,k", [(384, 10), (384, 50), (768, 100), (130, 10)])
+def test_single_process_shard_group_over_all_visible_gpus(sema, oracle_c, d, k):
+    """sema_shard_group_create_local: ONE process, ONE handle, one shard per visible GPU (the reference is a
+    single process owning a single StorageManager, src/storage/mod.rs:13-16).  Runs with however many GPUs
+    the box shows (1 on the default test box; `gpurun --gpus N` exercises the peer exchange for real)."""
+    from sema_b200 import _lib
+    from sema_b200.sharded import shard_range
+    G = min(_lib.lib().sema_device_count(), 8)
+    n = 60011
+    X = _unit(1, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::13] = 0
+    Q = _unit(2, 6, d)
+    shards = []
+    try:
+        for g in range(G):
+            lo, hi = shard_range(n, G, g)
+            idx = sema.GpuIndex(d, max(hi - lo, 1), device=g)
+            idx.set_row_base(lo)
+            if hi > lo:
+                idx.append(X[lo:hi], valid=valid[lo:hi], normalize=False)
+            shards.append(idx)
+        grp = sema.ShardGroup.local(shards)
+        try:
+            for q in Q:
+                ids, sc = grp.search(q, k)                           # one host call, G fused kernels
+                r_ids, r_sc = oracle_c.scan(X, q, k, valid=valid)
+                O.check_parity(ids, sc, r_ids, r_sc)
+            if d in (384, 768):                                      # submit / collect: several searches in flight
+                import ctypes as C
+                ids_h, sc_h = np.zeros(k, np.uint64), np.zeros(k, np.float32)
+                tickets = [grp.submit_ptr(C.c_void_p(Q[i].ctypes.data), k) for i in range(4)]
+                for i, t in enumerate(tickets):
+                    nf = grp.collect_ptr(t, C.c_void_p(ids_h.ctypes.data), C.c_void_p(sc_h.ctypes.data))
+                    r_ids, r_sc = oracle_c.scan(X, Q[i], k, valid=valid)
+                    O.check_parity(ids_h[:nf], sc_h[:nf], r_ids, r_sc)
+            # tombstones on one shard are seen by the next group search
+            dead = oracle_c.scan(X, Q[0], k, valid=valid)[0][:3]
+            for row in dead:
+                g = next(i for i in range(G) if shard_range(n, G, i)[0] <= row < shard_range(n, G, i)[1])
+                shards[g].tombstone(np.array([row - shard_range(n, G, g)[0]], dtype=np.uint64))
+            v2 = valid.copy()
+            v2[dead.astype(np.int64)] = 0
+            ids, sc = grp.search(Q[0], k)
+            r_ids, r_sc = oracle_c.scan(X, Q[0], k, valid=v2)
+            O.check_parity(ids, sc, r_ids, r_sc)
+            with pytest.raises(sema.SemaError):
+                grp.search(Q[0], 200)                                # the fused exchange covers k <= 128
+            import torch
+            qd = torch.from_numpy(Q[0]).cuda()
+            out = torch.zeros(k, dtype=torch.int64, device="cuda"), torch.zeros(k, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+            with pytest.raises(sema.SemaError):                      # device-resident queries live on one GPU
+                grp.search_device(qd.data_ptr(), k, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr())
+        finally:
+            grp.close()
+    finally:
+        for idx in shards:
+            idx.close()
+
+
+def test_single_process_shard_group_rejects_bad_arguments(sema):
+    a = sema.GpuIndex(384, 16)
+    b = sema.GpuIndex(384, 16)
+    c = sema.GpuIndex(768, 16)
+    try:
+        with pytest.raises(sema.SemaError):
+            sema.ShardGroup.local([a, b])                            # two shards on one device
+        if __import__("sema_b200")._lib.lib().sema_device_count() >= 2:
+            c2 = sema.GpuIndex(768, 16, device=1)
+            try:
+                with pytest.raises(sema.SemaError):
+                    sema.ShardGroup.local([a, c2])                   # dims differ
+            finally:
+                c2.close()
+    finally:
+        a.close(); b.close(); c.close()
+
+
 # ---------------------------------------------------------------- next rows: compaction, disk cache, Arrow
 def test_compaction_drops_dead_rows_and_keeps_order(sema, oracle_c):
     n, d, k = 20000, 384, 10
