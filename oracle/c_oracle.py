@@ -67,10 +67,29 @@ def set_threads(n: int) -> None:
     lib().sema_oracle_set_threads(int(n))
 
 
+def use_all_cores() -> int:
+    """One OpenMP thread per core this process may run on (sched_getaffinity), whatever
+    OMP_NUM_THREADS says — torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently
+    turn the timed CPU baseline into a single-threaded one.  Returns the thread count now in use."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    set_threads(max(n, 1))
+    return threads()
+
+
 def normalize(rows: np.ndarray) -> np.ndarray:
     x = np.array(rows, dtype=np.float32, copy=True, order="C")
     n, d = x.shape
     lib().sema_oracle_normalize(_p(x, C.c_float), n, d)
+    return x
+
+
+def normalize_inplace(x: np.ndarray) -> np.ndarray:
+    """normalize() without the copy (the 15 GB full-size corpora of bench.py / the full-size tests)."""
+    assert x.dtype == np.float32 and x.flags.c_contiguous and x.ndim == 2
+    lib().sema_oracle_normalize(_p(x, C.c_float), x.shape[0], x.shape[1])
     return x
 
 

@@ -98,9 +98,10 @@ def test_bench_reference_arm_prints_one_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-           "--cpu-rows", "20000"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0",
+           "--rows", "20000"]
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must not become single-threaded because of it
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert out.returncode == 0, out.stderr
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -109,7 +110,16 @@ def test_bench_reference_arm_prints_one_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert key in d, key
     assert d["impl"] == "reference" and d["gpu_launches"] == 0 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    # the whole corpus named in `config` is scanned, nothing is extrapolated, the step time is a measured one
+    assert d["cpu_baseline"]["extrapolated"] is False and d["config"]["rows"] == 20000 and d["steps"] == 2
+    assert abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
+    assert d["cpu_baseline"]["ms_per_scan_min"] <= d["ms_per_step"] <= d["cpu_baseline"]["ms_per_scan_max"] * 1.5
+    sys.path.insert(0, root)
+    import argparse
+    import bench
+    a = argparse.Namespace(rows=20000, dim=384, k=10, queries=64, gpus=1)
+    assert d["config"] == bench.shared_config(a)                 # both arms state the workload identically
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)

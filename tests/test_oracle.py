@@ -216,3 +216,43 @@ def test_mean_pool_golden_fixture(oracle_c):
     assert np.array_equal(O.mean_pool(g["tokens"], g["mask"]), g["pooled"])
     assert np.array_equal(oracle_c.mean_pool(g["tokens"], g["mask"]), g["pooled"])
     np.testing.assert_allclose(g["pooled"], g["pooled64"], rtol=2e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------ a third, independent implementation
+@pytest.mark.parametrize("n,d,k,metric", [(200_000, 384, 10, 0), (200_000, 384, 50, 1), (60_000, 768, 100, 0), (30_000, 130, 10, 1)])
+def test_oracles_agree_with_an_independent_float64_torch_implementation(oracle_c, n, d, k, metric):
+    """The oracle is the builder's restatement, and the golden fixtures are its own output; so it is also held
+    against code that shares nothing with it: torch's CPU GEMV and torch.topk in float64 (different summation
+    order, different selection algorithm, twice the precision).  BASELINE.json's rule must hold between them:
+    same ids and order except ties within 1e-5, scores within 1e-5 relative."""
+    import torch
+    X = oracle_c.normalize(oracle_c.synth(11, 0, n, d))
+    Q = oracle_c.normalize(oracle_c.synth(12, 0, 6, d))
+    valid = np.ones(n, np.uint8)
+    valid[::29] = 0
+    Xt = torch.from_numpy(X).double()
+    dead = torch.from_numpy(valid == 0)
+    for q in Q:
+        qt = torch.from_numpy(q).double()
+        if metric == 0:
+            s = Xt @ qt
+            s[dead] = -float("inf")
+            top = torch.topk(s, k)
+            t_ids, t_sc = top.indices.numpy().astype(np.uint64), top.values.numpy()
+        else:
+            s = ((Xt - qt) ** 2).sum(dim=1)
+            s[dead] = float("inf")
+            top = torch.topk(s, k, largest=False)
+            t_ids, t_sc = top.indices.numpy().astype(np.uint64), top.values.numpy()
+        c_ids, c_sc = oracle_c.scan(X, q, k, metric=metric, valid=valid)
+        O.check_parity(c_ids, c_sc, t_ids, t_sc)                    # C oracle vs the independent implementation
+        if n <= 60_000:
+            p_ids, p_sc = O.scan(X, q, k, metric=metric, valid=valid)
+            O.check_parity(p_ids, p_sc, t_ids, t_sc)                # NumPy oracle vs the independent implementation
+
+
+def test_normalize_agrees_with_float64_torch():
+    import torch
+    raw = O.synth(13, 0, 2000, 384)
+    want = torch.nn.functional.normalize(torch.from_numpy(raw).double(), dim=1).numpy()
+    np.testing.assert_allclose(O.normalize(raw), want, rtol=3e-6, atol=1e-9)   # fp32 sequential sum vs fp64: a few ulp
