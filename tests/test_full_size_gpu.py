@@ -112,7 +112,9 @@ def test_config5_streaming_ingest_768_k100_every_query_matches_oracle_on_its_sna
     d, k, B, nb = 768, 100, 65536, 16
     n = B * nb                                                                  # 1 048 576 rows
     oracle_c.use_all_cores()
-    raw = oracle_c.synth(7, 0, n, d)
+    import torch
+    raw_pinned = torch.from_numpy(oracle_c.synth(7, 0, n, d)).pin_memory()      # pinned: the H2D copies are truly asynchronous
+    raw = raw_pinned.numpy()
     X = oracle_c.normalize(raw)
     Q = oracle_c.normalize(oracle_c.synth(8, 0, 32, d))
     results = []
