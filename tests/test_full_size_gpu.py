@@ -119,9 +119,14 @@ def test_config5_streaming_ingest_768_k100_every_query_matches_oracle_on_its_sna
     Q = oracle_c.normalize(oracle_c.synth(8, 0, 32, d))
     results = []
     with sema.GpuIndex(d, n) as idx:
-        for b in range(nb):
+        # first batch synchronously + one search: the handle's one-time allocations (cudaMalloc / cudaHostAlloc
+        # synchronise the device) must not sit between the asynchronous appends and the first timed query
+        idx.append(raw[:B], normalize=True)
+        ids, sc = idx.search(Q[0], k)
+        results.append((0, idx.last_snapshot, ids, sc))
+        for b in range(1, nb):
             idx.append(raw[b * B:(b + 1) * B], normalize=True, asynchronous=True)
-        i = 0
+        i = 1
         while idx.visible < n:
             if idx.visible == 0:
                 continue
