@@ -64,7 +64,9 @@ def parse():
                          "config1 = ~10k-chunk synthetic markdown corpus through the StorageManager boundary; pool = K0")
     ap.add_argument("--ingest-batch", type=int, default=65536, help="rows per appended batch (--workload ingest)")
     ap.add_argument("--nq", type=int, default=1024, help="queries per batch (--workload batch)")
-    ap.add_argument("--batch-mode", type=int, default=2, help="0 auto (cascade), 1 K2 per query, 2 K3 bf16x3, 3 K3 single pass")
+    ap.add_argument("--batch-mode", type=int, default=2, help="0 auto (cascade), 1 K2 per query, 2 K3 three-pass split, 3 K3 single pass")
+    ap.add_argument("--precision", type=int, default=0, help="K3 split format: 0 automatic (fp16 halves on unit-norm rows), 1 bf16 halves")
+    ap.add_argument("--k3-pair", type=int, default=-1, help="K3 single-pass stage: 0 single-CTA kernel, 1 CTA pairs (default) (tuning)")
     ap.add_argument("--k3-cluster", type=int, default=0, help="K3 cluster size (0 auto, 1, 2, 4) — tuning")
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed whole-corpus CPU scans of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -424,18 +426,24 @@ def batch_measure(idx, Qd, nq, k, mode, steps, stream):
             nf_d.cpu().numpy())
 
 
-BATCH_MODES = {2: ("bf16x3", "3 x bf16 split passes (q_hi.x_hi + q_lo.x_hi + q_hi.x_lo) -> f32 accumulate, exact f32 re-scoring", 3.0),
-               3: ("bf16x1", "1 bf16 pass as candidate filter -> exact f32 re-scoring (+ K2 for unproven queries)", 1.0),
-               0: ("cascade", "1 bf16 pass -> bf16x3 only for queries the loose bound cannot prove -> K2; exact f32 re-scoring", 1.0)}
+def batch_modes(fmt):
+    """mode -> (name, dtype text, tensor passes issued); fmt = element format of the split (idx.batch_precision_active)."""
+    f = "fp16" if fmt == 1 else "bf16"
+    return {2: (f"{f}x3", f"3 x {f} split passes (q_hi.x_hi + q_lo.x_hi + q_hi.x_lo) -> f32 accumulate, exact f32 re-scoring", 3.0),
+            3: (f"{f}x1", f"1 {f} pass as candidate filter -> exact f32 re-scoring (+ K2 for unproven queries)", 1.0),
+            0: ("cascade", f"1 {f} pass -> {f}x3 only for queries the loose bound cannot prove -> K2; exact f32 re-scoring", 1.0)}
 
 
-def batch_record(rows, dim, nq, k, mode, ms, launches, stats):
+BATCH_MODES = batch_modes(0)
+
+
+def batch_record(rows, dim, nq, k, mode, ms, launches, stats, fmt=0):
     peaks, src = load_peaks()
     peak = float(peaks.get("bf16_tflops", 1590.0))
     sustained = peaks.get("bf16_tflops_sustained")
     flop = 2.0 * nq * rows * dim
     ach = flop / (ms * 1e-3) / 1e12
-    name, dtype, passes = BATCH_MODES[mode]
+    name, dtype, passes = batch_modes(fmt)[mode]
     return {"mode": name, "dtype": dtype, "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms,
             "gpu_launches_per_batch": launches,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -456,10 +464,14 @@ def sub_batch(a, idx, hc, dev, stream, k2_ids, k2_sc):
     Qd = torch.from_numpy(Q).to(dev)
     out = {"workload": f"{a.rows}x{a.dim} fp32 corpus, batches of {nq} queries, exact top-{k} (BASELINE configs[2])",
            "metric": f"qps_batched_{nq}q_exact_top{k}_cosine_{a.rows}x{a.dim}_fp32", "modes": {}}
-    for mode in (2, 0):
+    # the three-pass split and the cascade in the default element format (fp16 halves on unit-norm rows), then the
+    # three-pass split with bf16 halves (the north star's 3 x bf16 by name)
+    for prec, mode in ((0, 2), (0, 0), (1, 2)):
+        idx.set_batch_precision(prec)
         q0, f0 = idx.batch_stats()
         c0 = idx.batch_cascaded
         ms, launches, ids, sc, nf = batch_measure(idx, Qd, nq, k, mode, 6, stream)
+        fmt = idx.batch_precision_active
         q1, f1 = idx.batch_stats()
         batches = max((q1 - q0) // nq, 1)
         fails = []
@@ -473,9 +485,12 @@ def sub_batch(a, idx, hc, dev, stream, k2_ids, k2_sc):
                  "oracle_checked_queries": 0 if hc is None else N_ORACLE_QUERIES, "oracle_failures": fails,
                  "bit_identical_to_k2_on_first_queries": same_as_k2,
                  "verified": (not fails and same_as_k2 is not False) if (hc is not None or same_as_k2 is not None) else None}
-        out["modes"][BATCH_MODES[mode][0]] = batch_record(a.rows, a.dim, nq, k, mode, ms, launches, stats)
+        rec = batch_record(a.rows, a.dim, nq, k, mode, ms, launches, stats, fmt)
+        out["modes"][rec["mode"]] = rec
+    idx.set_batch_precision(0)
     idx.set_batch_mode(0)
-    out["value"] = out["modes"]["bf16x3"]["value"]
+    out["value"] = out["modes"]["cascade"]["value"]           # what sema_index_search_batch does by default
+    out["value_is"] = "cascade (automatic mode, the call's default); the pure three-pass splits are listed beside it"
     out["unit"] = "queries/s"
     out["verified"] = all(m["verified"] is not False for m in out["modes"].values())
     return out
@@ -1020,6 +1035,9 @@ def run_batch(a):
     idx.append_synthetic(seed=1, row0=0, n=a.rows, normalize=True)
     if a.k3_cluster:
         idx.set_scan_variant(100 + a.k3_cluster)
+    if a.k3_pair >= 0:
+        idx.set_scan_variant(700 + a.k3_pair)
+    idx.set_batch_precision(a.precision)
     Q = make_queries(nq, a.dim, 0)
     stream = torch.cuda.current_stream()
     Qd = torch.from_numpy(Q).to(dev)
@@ -1039,14 +1057,15 @@ def run_batch(a):
         r_ids, r_sc = idx.search(Q[i], k)
         ok &= bool(np.array_equal(ids_h[i, :nf_h[i]], r_ids) and np.array_equal(sc_h[i, :nf_h[i]], r_sc))
     rec = batch_record(a.rows, a.dim, nq, k, a.batch_mode if a.batch_mode in BATCH_MODES else 2, ms, launches,
-                       {"k3_queries": served, "k3_fallback_queries": fallbacks, "cascaded_queries": idx.batch_cascaded})
+                       {"k3_queries": served, "k3_fallback_queries": fallbacks, "cascaded_queries": idx.batch_cascaded},
+                       idx.batch_precision_active)
     line = {
         "metric": f"qps_batched_{nq}q_exact_top{k}_cosine_{a.rows}x{a.dim}_fp32", "value": rec["value"],
         "unit": "queries/s", "n_gpus": 1, "steps": steps, "warmup": 3, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": rec["dtype"], "data": "synthetic",
         "config": {"workload": f"{a.rows}x{a.dim} fp32 corpus, batches of {nq} queries, exact top-{k} (BASELINE configs[2])",
-                   "batch_mode": rec["mode"], "k3_cluster": a.k3_cluster or "auto",
-                   "l2_flush": "none needed: each batch streams the bf16 planes of the whole corpus"},
+                   "batch_mode": rec["mode"], "k3_cluster": a.k3_cluster or "auto", "k3_pair": "default (CTA pairs)" if a.k3_pair < 0 else a.k3_pair,
+                   "l2_flush": "none needed: each batch streams the 16-bit planes of the whole corpus"},
         "roofline": rec["roofline"], "batch": rec,
         "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * a.dim * 4,
                 "d2h_bytes_per_step": nq * (k * 12 + 4), "ms_per_step": e2e_ms,

@@ -161,8 +161,8 @@ int sema_index_search_collect(sema_index *idx, uint64_t ticket, uint64_t *row_id
  * dim % 64 == 0, dim <= 768, k <= 100, nq >= 4 and either the cosine metric or the L2 metric over
  * rows of (nearly) constant norm — the reference's case: unit-norm rows under LanceDB's default
  * squared-L2 `_distance` — this runs kernel K3 (tcgen05
- * tensor cores, bf16 split precision — see sema_index_set_batch_mode — with exact fp32
- * re-scoring of the candidates; needs a second dim*4 bytes per row of HBM for the bf16 planes,
+ * tensor cores, 16-bit split precision — see sema_index_set_batch_mode / _set_batch_precision — with exact fp32
+ * re-scoring of the candidates; needs a second dim*4 bytes per row of HBM for the 16-bit hi/lo planes,
  * built on first use); otherwise, or if that memory cannot be had, K2 runs once per query.
  * Results are identical either way. */
 int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32_t k,
@@ -184,13 +184,23 @@ int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t
 int sema_index_search_stream_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
                                     uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
 /* mode 0 = automatic: when the shape allows and nq >= 4, a precision cascade on the tensor cores —
- * a single bf16 pass as a coarse candidate filter (a third of the tensor work), then the bf16x3
- * split for the queries whose exactness proof failed under the looser single-pass error bound,
- * then K2 for the few neither can prove (exact ties beyond the candidate list);
- * 1 = always K2 per query; 2 = K3 bf16x3 only (+ K2 fallback); 3 = K3 single pass only (+ K2
+ * a single 16-bit pass (q_hi . x_hi) as a coarse candidate filter (a third of the tensor work), then the
+ * three-pass error-compensated split (q_hi.x_hi + q_lo.x_hi + q_hi.x_lo) for the queries whose exactness
+ * proof failed under the looser single-pass error bound, then K2 for the few neither can prove (exact
+ * ties beyond the candidate list);
+ * 1 = always K2 per query; 2 = K3 three-pass split only (+ K2 fallback); 3 = K3 single pass only (+ K2
  * fallback).  Every path ends in the same exact fp32 re-scoring: results are identical.  Other
  * values only query.  Returns the mode now active. */
 int sema_index_set_batch_mode(sema_index *idx, int mode);
+/* Element format of the split: 0 = automatic (default) — fp16 halves (11 significant bits: per-stage error
+ * bounds 1.15e-3 / 2.0e-4 of |q||x| for one / three passes) whenever every stored element is at most 1024 in
+ * magnitude (max |x|^2 <= 2^20; queries of any magnitude are scaled by a power of two inside the kernel),
+ * bf16 halves (8 significant bits, fp32's range: 8.5e-3 / 2.5e-4) otherwise; 1 = bf16 always (the 3 x bf16 split
+ * by name).  Either way the tensor-core pass only selects candidates; results are identical.  The planes are
+ * re-split (one read + one write of the corpus) when the active format changes.  Other values only query.
+ * Returns the preference now set; _active returns the format the planes are in (0 bf16, 1 fp16, -1 none built yet). */
+int sema_index_set_batch_precision(sema_index *idx, int prec);
+int sema_index_batch_precision_active(const sema_index *idx);
 /* queries served by K3 so far; how many of them were re-run through K2 because exactness could not
  * be proven from the candidate lists (heavy ties / duplicates); how many went from the single-pass
  * stage to the bf16x3 stage in automatic mode.  Any pointer may be NULL. */
@@ -292,14 +302,17 @@ int sema_index_set_normalize_queries(sema_index *idx, int on);
 uint64_t sema_index_last_snapshot(const sema_index *idx);
 /* copy stored (normalised) rows back to the host: out = n x dim floats */
 int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float *out);
-/* Tuning knob for measurements (results never change).  0 = default K2 kernel (TMA bulk-copy ring
- * for dim 384 / 768), 1 / 2 / 3 = the register-fed K2 kernel with 4 / 2 / 8 rows per warp batch;
- * 100 + c = K3 cluster size c (0 = automatic); 200 / 201 = K3 two / one query tiles per CTA in the
- * single-pass stage; 300 + d = K3 timing probes (d = 1..3: wrong results, timing only; 8 = epilogue
- * without its group early-out, correct results); 400 / 401 = K3
- * single-pass candidate lists of 32 / 16 for k <= 10; 500 / 501 = host searches staged through
- * H2D + D2H copies / query by kernel parameter + results to mapped host memory (default);
- * 600 / 601 = query streams unchained / chained (default); negative = query.  Returns the value set. */
+/* Tuning knob for measurements.  NO setting changes a result: every value selects among kernels / launch shapes
+ * that produce identical output (the work-skipping timing probes of earlier versions are compiled out of this
+ * library; they exist only in the separate probe build made by scripts/build_probe.sh and are refused here).
+ * 0 = default K2 kernel (TMA bulk-copy ring for dim 384 / 768), 1 / 2 / 3 = the register-fed K2 kernel with
+ * 4 / 2 / 8 rows per warp batch; 100 + c = K3 cluster size c of the single-CTA kernels (0 = automatic);
+ * 200 / 201 = K3 two / one query tiles per CTA in the single-CTA single-pass kernel; 300 / 308 = K3 epilogue
+ * with / without its group early-out; 400 / 401 = K3 single-pass candidate lists of 32 / 16 for k <= 10;
+ * 500 / 501 = host searches staged through H2D + D2H copies / query by kernel parameter + results to mapped
+ * host memory (default); 600 / 601 = query streams unchained / chained (default); 700 / 701 / 702 = K3
+ * single-pass stage on the single-CTA kernel / on CTA pairs (tcgen05 cta_group::2, default) / on clusters of two
+ * pairs with multicast; negative = query.  Returns the value set, or -1 for a value this build does not have. */
 int sema_index_set_scan_variant(sema_index *idx, int variant);
 /* number of kernels this handle has launched so far */
 uint64_t sema_index_launch_count(const sema_index *idx);

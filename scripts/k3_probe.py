@@ -1,10 +1,15 @@
-"""K3 epilogue timing probes (debug flags give wrong results; timing only)."""
+"""K3 timing probes.  Needs the probe build (`make -C sema_b200/csrc PROBE=1`, loaded through SEMA_B200_LIB):
+the debug flags skip work and give wrong results, which the shipped library refuses.
+  pair kernel (variant 701 / 702): 1 = no scan (ld + release only), 2 = mask pass only, 16 = no tcgen05.ld either,
+  32 = no MMAs (TMA + barriers only), 8 = no group early-out (correct)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("SEMA_B200_LIB", os.path.join(ROOT, "sema_b200", "libsema_b200_probe.so"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import sema_b200
 from sema_b200.synth import synth_rows
-rows, nq, k = 10_000_000, 1024, 10
+rows, nq, k = int(os.environ.get("ROWS", 10_000_000)), 1024, 10
 dev = torch.device("cuda:0")
 idx = sema_b200.GpuIndex(384, rows)
 idx.append_synthetic(1, 0, rows, True)
@@ -13,18 +18,16 @@ with sema_b200.GpuIndex(384, nq) as qi:
 stream = torch.cuda.current_stream(); idx.set_stream(stream.cuda_stream)
 Qd = torch.from_numpy(Q).to(dev)
 ids_d = torch.zeros(nq * k, dtype=torch.int64, device=dev); sc_d = torch.zeros(nq * k, dtype=torch.float32, device=dev); nf_d = torch.zeros(nq, dtype=torch.int32, device=dev)
-def run(mode, dbg):
-    idx.set_batch_mode(mode); idx.set_scan_variant(300 + dbg)
+def run(mode, variant, dbg, reps=4):
+    idx.set_batch_mode(mode); idx.set_scan_variant(variant); assert idx.set_scan_variant(1000000 + dbg) == 1000000 + dbg
     for _ in range(2): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(3): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+    for _ in range(reps): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     e1.record(stream); torch.cuda.synchronize()
-    print(f"mode={mode} debug={dbg}: {e0.elapsed_time(e1)/3:.2f} ms   (0 full, 1 no scan, 2 mask pass only, 3 inserts without rescan)", flush=True)
-for kc16 in (0, 1):
-    idx.set_scan_variant(400 + kc16)
-    print('kc16 =', kc16)
-    for dbg in (0, 1, 2):
-        run(3, dbg)
-    run(0, 0)
+    print(f"mode={mode} variant={variant} debug={dbg:2d}: {e0.elapsed_time(e1)/reps:.3f} ms", flush=True)
+for rnd in range(3):
+    for dbg in (0, 8, 2, 1, 17, 49):
+        run(3, 701, dbg, reps=3)
+    run(3, 700, 0, reps=3)

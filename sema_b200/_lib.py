@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsema_b200.so")
+# SEMA_B200_LIB: another build of the same library (scripts/k3_probe.py points it at the probe build)
+SO_PATH = os.environ.get("SEMA_B200_LIB") or os.path.join(_HERE, "libsema_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sema_b200.h")
 
 SEMA_OK = 0
@@ -56,6 +57,8 @@ SIGNATURES = {
     "sema_index_search_stream_device": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
     "sema_index_set_normalize_queries": (C.c_int, [_vp, C.c_int]),
     "sema_index_set_batch_mode": (C.c_int, [_vp, C.c_int]),
+    "sema_index_set_batch_precision": (C.c_int, [_vp, C.c_int]),
+    "sema_index_batch_precision_active": (C.c_int, [_vp]),
     "sema_index_batch_stats": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "sema_index_search_keys_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "sema_index_search_device": (C.c_int, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),

@@ -1,6 +1,7 @@
 // api_batch.cu — K3: bf16 planes, cluster launch, exact re-scoring, K2 fallback; batched entry points.
 #include "index_impl.cuh"
 #include "k3_batch.cuh"
+#include "k3_pair.cuh"
 #include "k4_merge.cuh"
 
 using namespace sema;
@@ -10,8 +11,26 @@ namespace {
 
 // ---- K3 dispatch -----------------------------------------------------------------
 constexpr uint32_t K3_MAX_K = 100;
-constexpr float K3_ERR_REL = 2.5e-4f;  // >= 3*2^-16 (dropped split terms) + fp32 accumulation over 3*dim terms
-constexpr float K3_ERR_REL_1PASS = 8.5e-3f;  // >= 2*2^-8 + 2^-16 (both operands rounded to bf16) + accumulation
+// |tensor-core score - exact score| <= err_rel * |q| * max|x| + err_abs * |q|   (unit roundoff u = 2^-8 bf16, 2^-11 fp16)
+//   3 passes (hi.hi + lo.hi + hi.lo): 3 u^2 (dropped lo.lo term and the residuals of the two-term splits) + fp32
+//   accumulation over 3*dim <= 1152 products (allowance 2e-4);  1 pass: 2u + u^2 (both operands rounded) + accumulation
+//   over dim <= 768 products (allowance 1.4e-4).
+//   fp16 only: elements below 2^-14 are subnormal and carry an ABSOLUTE error <= 2^-25 per element and term instead
+//   of a relative one: <= 3 * 2^-25 * sqrt(dim) * |q| over a row (queries are scaled into [0.5, 1), where the same
+//   term is <= 2^-24 * sqrt(dim) * |q||x| and is part of err_rel's slack).
+constexpr float K3_ERR_REL_BF16X3 = 2.5e-4f;
+constexpr float K3_ERR_REL_BF16X1 = 8.5e-3f;
+constexpr float K3_ERR_REL_FP16X3 = 2.0e-4f;
+constexpr float K3_ERR_REL_FP16X1 = 1.15e-3f;
+inline float k3_err_rel(int fmt, int passes)
+{
+    if (fmt == k3::FMT_FP16) return passes == 1 ? K3_ERR_REL_FP16X1 : K3_ERR_REL_FP16X3;
+    return passes == 1 ? K3_ERR_REL_BF16X1 : K3_ERR_REL_BF16X3;
+}
+inline float k3_err_abs(int fmt, uint32_t dim)
+{
+    return fmt == k3::FMT_FP16 ? 3.0f * 2.98023224e-8f * sqrtf((float)dim) : 0.0f;
+}
 
 // passes the batch would run with: bf16x3 up to dim 384 (TMEM holds q_hi and q_lo), the single-pass
 // filter up to dim 768 (q_hi only) or when asked for (batch mode 3); 0 = K3 cannot serve this shape
@@ -37,9 +56,29 @@ int k3_check_norms(sema_index *s)
     return SEMA_OK;
 }
 
-// Bring the bf16 planes up to date with rows [0, n).  Tombstones invalidate from their row on.
+// Element format of the planes.  fp16 (11 significant bits) gives every stage an 8x tighter error bound than bf16
+// at the same tensor-core cost, but its range is narrow: it is used when every stored element is <= 1024 in
+// magnitude (max |x|^2 <= 2^20 — the reference's unit-norm rows by a wide margin); otherwise bf16.
+int k3_choose_fmt(sema_index *s, int *fmt)
+{
+    if (s->k3_prec == 1) { *fmt = k3::FMT_BF16; return SEMA_OK; }
+    float mm[2] = {0.0f, 0.0f};
+    CK(cudaMemcpyAsync(mm, s->max_norm2, sizeof mm, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *fmt = (mm[0] <= 1048576.0f) ? k3::FMT_FP16 : k3::FMT_BF16;
+    return SEMA_OK;
+}
+
+// Bring the 16-bit planes up to date with rows [0, n).  Tombstones are poisoned in place (k3_poison_rows).
 int k3_sync_planes(sema_index *s, uint64_t n)
 {
+    if (!s->planes || s->planes_rows < n || s->planes_prec != s->k3_prec) {   // new rows (or a new preference): (re)decide the format
+        int fmt = k3::FMT_BF16;
+        int rc = k3_choose_fmt(s, &fmt);
+        if (rc) return rc;
+        if (fmt != s->planes_fmt) { s->planes_fmt = fmt; s->planes_rows = 0; }   // re-split everything in the other format
+        s->planes_prec = s->k3_prec;
+    }
     if (!s->planes) {
         const uint64_t tiles = (s->capacity + k3::TILE_N - 1) / k3::TILE_N;
         const size_t bytes = (size_t)(tiles ? tiles : 1) * k3::tile_bytes((int)s->dim);
@@ -72,7 +111,7 @@ int k3_sync_planes(sema_index *s, uint64_t n)
     const uint64_t work = (end - begin) * (s->dim / 8);
     uint64_t blocks = (work + 255) / 256;
     if (blocks > (uint64_t)s->num_sms * 32) blocks = (uint64_t)s->num_sms * 32;
-    k3::split_planes_kernel<<<(unsigned)blocks, 256, 0, s->stream>>>(s->X, s->ld, s->dim, begin, end, n, s->planes);
+    k3::split_planes_kernel<<<(unsigned)blocks, 256, 0, s->stream>>>(s->X, s->ld, s->dim, begin, end, n, s->planes, s->planes_fmt);
     CK(cudaGetLastError());
     s->launches++;
     s->planes_rows = n;
@@ -138,6 +177,99 @@ int k3_max_clusters(sema_index *s, int *out)
     return SEMA_OK;
 }
 
+// ---- CTA-pair form of the single-pass stage (k3_pair.cuh): grid (query tiles, parts), clusters of 2 CTAs
+inline int k3_pair_smem(int kc, uint32_t dim)
+{
+    const int need = k3::pair_smem_bytes(kc, (int)dim);
+    return need < 116 * 1024 ? 116 * 1024 : need;      // never two CTAs per SM: each allocates all 512 TMEM columns
+}
+// The planes as the pair kernel's 3-D tensor: 8-byte elements, {256 (one 2 KB row), 4 (rows of an 8 KB hi block),
+// groups of 16 KB (the hi|lo pair of one k-block of one tile)}; box = the hi blocks of pair_kps(dim) consecutive
+// k-blocks.  Encoded once per planes allocation (the growable index reserves its whole address range up front).
+int k3_pair_tmap(sema_index *s)
+{
+    if (s->tmap_base == s->planes) return SEMA_OK;
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            return fail(SEMA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const uint64_t tiles = (s->capacity + k3::TILE_N - 1) / k3::TILE_N;
+    const cuuint64_t gdim[3] = {256, 4, (tiles ? tiles : 1) * (s->dim / k3::BLOCK_K)};
+    const cuuint64_t gstride[2] = {2048, (cuuint64_t)k3::STAGE_BYTES};
+    const cuuint32_t box[3] = {256, 4, (cuuint32_t)k3::pair_kps((int)s->dim)};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult r = encode(&s->planes_tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, s->planes, gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SEMA_ERR_CUDA, "cuTensorMapEncodeTiled failed for the K3 planes (CUresult %d)", (int)r);
+    s->tmap_base = s->planes;
+    return SEMA_OK;
+}
+
+template <int KC>
+int k3_launch_pair(sema_index *s, const k3::Params &p, uint32_t q_tiles)
+{
+    int trc = k3_pair_tmap(s);
+    if (trc) return trc;
+    auto kern = k3::pair_scan_kernel<KC>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[s->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[s->device & 63] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(q_tiles, p.parts, 1);
+    cfg.blockDim = dim3(k3::PAIR_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)k3_pair_smem(KC, p.dim);
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, p, s->planes_tmap));
+    s->launches++;
+    return SEMA_OK;
+}
+template <int KC>
+int k3_pair_clusters(sema_index *s, int *out)
+{
+    static int cached[64] = {0};
+    int &v = cached[s->device & 63];
+    if (v == 0) {
+        auto kern = k3::pair_scan_kernel<KC>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2, (unsigned)s->num_sms, 1);
+        cfg.blockDim = dim3(k3::PAIR_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = 227 * 1024;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        CK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        v = n > 0 ? n : 1;
+    }
+    *out = v;
+    return SEMA_OK;
+}
+
 template <int KC, int PASSES, int QT>
 int k3_launch_scan_p(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c)
 {
@@ -176,12 +308,17 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     // csize CTAs along the query axis: the query-tile count is padded to a multiple of QT*csize
     // (Qpad rows beyond nq are zero queries whose results are never read).
     // (two tiles need 2*dim/2 + 128 TMEM columns and two candidate lists in shared memory)
-    const int qt_per_cta = (passes == 1 && q_tiles_all >= 2 && s->k3_qt != 1 && s->dim <= 384 && kc <= 64) ? 2 : 1;
+    // The single-pass stage runs as CTA pairs (k3_pair.cuh: tcgen05 cta_group::2, M = 256 x N = 128) whenever there
+    // are at least two query tiles and the queries plus two 128-column accumulators fit TMEM; pp = pairs per cluster.
+    const bool pair = passes == 1 && s->k3_pair != 0 && q_tiles_all >= 2 && s->dim <= (uint32_t)k3::PAIR_MAX_DIM && kc <= 64 &&
+                      k3::pair_stages((int)kc, (int)s->dim) >= 2 * k3::pair_spt((int)s->dim);
+    const int qt_per_cta = pair ? 1 : ((passes == 1 && q_tiles_all >= 2 && s->k3_qt != 1 && s->dim <= 384 && kc <= 64) ? 2 : 1);
     const uint32_t q_ctas_all = (q_tiles_all + qt_per_cta - 1) / qt_per_cta;
     // measured on 10M x 384 x 1024q: bf16x3 is fastest with clusters of 4 (128 SMs, higher clocks under the
     // power cap), the single-pass filter with clusters of 2 (144 SMs; it is bound by L2->SM delivery)
     const int cpref = passes == 1 ? 2 : 4;
-    const int csize = s->k3_cluster > 0 ? s->k3_cluster : (q_ctas_all >= (uint32_t)cpref ? cpref : (q_ctas_all >= 2 ? 2 : 1));
+    const int csize = pair ? 2
+                           : (s->k3_cluster > 0 ? s->k3_cluster : (q_ctas_all >= (uint32_t)cpref ? cpref : (q_ctas_all >= 2 ? 2 : 1)));
     const uint32_t q_ctas_pad = ((q_ctas_all + csize - 1) / csize) * csize;
     const size_t qpad_rows = (size_t)q_ctas_pad * qt_per_cta * k3::TILE_Q;
     rc = ensure(reinterpret_cast<void **>(&s->Qpad_dev), &s->qpad_cap, qpad_rows * s->dim * sizeof(float));
@@ -197,7 +334,10 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     CK(cudaMemcpyAsync(s->Qpad_dev, Qd, (size_t)nq * s->dim * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
 
     int max_clusters = 1;
-    rc = kc == 16 ? k3_clusters<16>(s, csize, &max_clusters) : kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
+    if (pair)
+        rc = kc == 16 ? k3_pair_clusters<16>(s, &max_clusters) : kc == 32 ? k3_pair_clusters<32>(s, &max_clusters) : k3_pair_clusters<64>(s, &max_clusters);
+    else
+        rc = kc == 16 ? k3_clusters<16>(s, csize, &max_clusters) : kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
     if (rc) return rc;
     const uint32_t groups_all = q_ctas_pad / csize;             // clusters along the query axis
     // at most max_clusters cluster columns per launch; the clusters left over become row partitions
@@ -223,9 +363,13 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         p.n_tiles = n_tiles;
         p.parts = parts;
         p.dim = s->dim;
+        p.fmt = (uint32_t)s->planes_fmt;
         p.debug = (uint32_t)s->k3_debug;
-        rc = kc == 16 ? k3_launch_scan<16>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, csize, passes, qt_per_cta)
-                      : k3_launch_scan<128>(s, p, q_ctas, csize, passes, qt_per_cta);
+        if (pair)
+            rc = kc == 16 ? k3_launch_pair<16>(s, p, q_ctas) : kc == 32 ? k3_launch_pair<32>(s, p, q_ctas) : k3_launch_pair<64>(s, p, q_ctas);
+        else
+            rc = kc == 16 ? k3_launch_scan<16>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, csize, passes, qt_per_cta)
+                          : k3_launch_scan<128>(s, p, q_ctas, csize, passes, qt_per_cta);
         if (rc) return rc;
         const uint32_t q_first = qt0 * k3::TILE_Q;
         if (q_first >= nq) break;
@@ -246,7 +390,8 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         r.kc = kc;
         r.row_base = s->row_base;
         r.max_norm2 = s->max_norm2;
-        r.err_rel = passes == 1 ? K3_ERR_REL_1PASS : K3_ERR_REL;
+        r.err_rel = k3_err_rel(s->planes_fmt, passes);
+        r.err_abs = k3_err_abs(s->planes_fmt, s->dim);
         if (s->metric == SEMA_METRIC_L2) {
             if (k <= 32) k3::rescore_kernel<1, METRIC_L2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);
             else if (k <= 64) k3::rescore_kernel<2, METRIC_L2><<<q_cnt, SCAN_THREADS, 0, s->stream>>>(r);

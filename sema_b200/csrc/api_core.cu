@@ -655,14 +655,39 @@ uint64_t sema_index_launch_count(const sema_index *s) { return s ? s->launches :
 int sema_index_set_scan_variant(sema_index *s, int variant)
 {
     if (!s) return -1;
+#ifdef SEMA_K3_PROBES
+    if (variant >= 1000000) { s->k3_debug = variant - 1000000; return variant; }   // probe builds: wide probe masks
+#endif
+    if (variant >= 800) return -1;
+    if (variant >= 702) return -1;
+    if (variant >= 700) { s->k3_pair = variant - 700; return variant; }      // 700 = single-CTA kernel for the single-pass stage, 701 = CTA pairs (default)
     if (variant >= 600) { s->chain = variant - 600; return variant; }        // 600 / 601 = query streams unchained / chained (PDL)
     if (variant >= 500) { s->host_path = variant - 500; return variant; }    // 500 / 501 = host searches staged through H2D + D2H / query by kernel parameter + mapped results
     if (variant >= 400) { s->k3_kc16 = variant - 400; return variant; }      // 400 = lists of 32, 401 = lists of 16 (k <= 10, single pass)
-    if (variant >= 300) { s->k3_debug = variant - 300; return variant; }     // timing experiments only
+    if (variant >= 300) {                                                    // 300 = default, 308 = epilogue without its group early-out (same results)
+#ifndef SEMA_K3_PROBES
+        if (variant != 300 && variant != 308) return -1;                     // the work-skipping timing probes exist only in probe builds
+#endif
+        s->k3_debug = variant - 300;
+        return variant;
+    }
     if (variant >= 200) { s->k3_qt = variant - 200; return variant; }        // 200 = auto, 201 = one query tile per CTA
     if (variant >= 100) { s->k3_cluster = variant - 100; return variant; }   // 100 = auto, 101/102/104 = K3 cluster size
     if (variant >= 0) s->variant = variant;
     return s->variant;
+}
+
+int sema_index_set_batch_precision(sema_index *s, int prec)
+{
+    if (!s) return -1;
+    if (prec == 0 || prec == 1) s->k3_prec = prec;
+    return s->k3_prec;
+}
+
+int sema_index_batch_precision_active(const sema_index *s)
+{
+    if (!s || !s->planes || s->planes_rows == 0) return -1;
+    return s->planes_fmt;
 }
 
 int sema_index_read_rows(sema_index *s, uint64_t first_row, uint64_t n, float *out)

@@ -120,6 +120,12 @@ struct sema_index {
     int k3_debug = 0;                   // timing experiments only (wrong results): see k3::Params::debug
     int k3_kc16 = 1;                    // single-pass stage with k <= 10 keeps 16 candidates per list (0 = 32) — tuning
     int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
+    int k3_pair = 1;                    // single-pass stage: 1 = CTA pairs (cta_group::2), 0 = the single-CTA kernel — tuning
+    int k3_prec = 0;                    // plane format preference: 0 = automatic (fp16 when every |x_i| <= 1024, else bf16), 1 = bf16 always
+    int planes_fmt = 0;                 // format the planes are in now (k3::FMT_BF16 / FMT_FP16)
+    int planes_prec = 0;                // the preference they were built under
+    CUtensorMap planes_tmap;            // the planes as a 3-D tensor for the CTA-pair kernel's cta_group::2 loads (k3_pair.cuh)
+    const void *tmap_base = nullptr;    // planes pointer the map was encoded for (nullptr = none yet)
     bool l2_norms_constant = false;     // L2 metric: row norms nearly constant, so K3's dot-product selection ranks like the distance
     int normalize_queries = 0;          // apply K1 to host queries before scanning
     unsigned char *qscratch = nullptr;  // [valid byte x MAXQ pad][float max_norm2 scratch][K0 text counters: +8 query stream, +16 ingest stream]

@@ -31,6 +31,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4), warp 6 = MMA issuer 1.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "k2_scan.cuh"
 #include "ptx.cuh"
@@ -51,6 +52,19 @@ constexpr int EPI_THREADS = 128;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_DIM = 384;           // bf16x3: q_hi + q_lo need dim TMEM columns; 128 are the accumulators
 constexpr int MAX_DIM_1PASS = 768;     // single pass: q_hi alone needs dim/2 columns
+
+// 16-bit element format of the planes and of the TMEM-resident queries (Params::fmt, idesc a/b format)
+constexpr int FMT_BF16 = 0;            // 8 significant bits, fp32's exponent range: any finite corpus
+constexpr int FMT_FP16 = 1;            // 11 significant bits: 8x tighter error bounds; needs |x_i| <= 1024 (queries are
+                                       // scaled by a power of two in the kernel, rows are checked by the host)
+
+// Timing probes (Params::debug values that skip work and therefore give WRONG results) exist only in
+// builds made with -DSEMA_K3_PROBES (scripts/build_probe.sh); the shipped library ignores them.
+#ifdef SEMA_K3_PROBES
+constexpr bool PROBES = true;
+#else
+constexpr bool PROBES = false;
+#endif
 
 // bytes of the pre-tiled planes per 64-row tile
 __host__ __device__ constexpr size_t tile_bytes(int dim) { return (size_t)TILE_N * dim * 4; }
@@ -123,19 +137,40 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo
     return d;                // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
 }
 
-// instruction descriptor: c=f32, a=b=bf16, both K-major, M=128, N=64, dense
-__host__ __device__ constexpr uint32_t make_idesc()
+// instruction descriptor: c = f32, a = b = bf16 (format 1) or fp16 (format 0), both K-major, dense, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int m, int n)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_Q >> 4) << 24);
+    const uint32_t ab = fmt == FMT_FP16 ? 0u : 1u;
+    return (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem)
+// two consecutive elements rounded to the 16-bit format (round to nearest even), packed low | high
+__device__ __forceinline__ uint32_t pack16(int fmt, float lo_elem, float hi_elem)
 {
-    const uint32_t a = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo_elem));
-    const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi_elem));
+    uint32_t a, b;
+    if (fmt == FMT_FP16) {
+        a = (uint32_t)__half_as_ushort(__float2half_rn(lo_elem));
+        b = (uint32_t)__half_as_ushort(__float2half_rn(hi_elem));
+    } else {
+        a = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo_elem));
+        b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi_elem));
+    }
     return a | (b << 16);
 }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float round16(int fmt, float x)
+{
+    return fmt == FMT_FP16 ? __half2float(__float2half_rn(x)) : __bfloat162float(__float2bfloat16_rn(x));
+}
+// power of two s with max|q_i| * s in [0.5, 1): keeps a query of any magnitude inside fp16's range (exact: only
+// the exponent changes); 1 for a zero or non-finite query
+__device__ __forceinline__ float query_scale(float amax)
+{
+    if (!(amax > 0.0f) || !(amax < INFINITY)) return 1.0f;
+    int e;
+    frexpf(amax, &e);                       // amax = f * 2^e, f in [0.5, 1)
+    e = e > 120 ? 120 : (e < -120 ? -120 : e);
+    return ldexpf(1.0f, -e);
+}
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 {
@@ -170,7 +205,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
 // One thread per (row, 8-element k-chunk); consecutive threads write consecutive 16 B.
 __global__ void __launch_bounds__(256)
 split_planes_kernel(const float *X, uint32_t ld, uint32_t dim, uint64_t row_begin, uint64_t row_end,
-                    uint64_t n_valid_rows, unsigned char *planes)
+                    uint64_t n_valid_rows, unsigned char *planes, int fmt)
 {
     const uint32_t chunks = dim / 8;
     const uint64_t total = (row_end - row_begin) * chunks;
@@ -196,9 +231,9 @@ split_planes_kernel(const float *X, uint32_t ld, uint32_t dim, uint64_t row_begi
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float h0 = bf16_round(v[2 * e]), h1 = bf16_round(v[2 * e + 1]);
-            hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-            lo[e] = pack_bf16(v[2 * e] - h0, v[2 * e + 1] - h1);
+            const float h0 = round16(fmt, v[2 * e]), h1 = round16(fmt, v[2 * e + 1]);
+            hi[e] = pack16(fmt, v[2 * e], v[2 * e + 1]);
+            lo[e] = pack16(fmt, v[2 * e] - h0, v[2 * e + 1] - h1);
         }
         const uint64_t tile = (row_begin / TILE_N) + t;
         unsigned char *base = planes + tile * tile_bytes((int)dim) + (size_t)(c / 8) * STAGE_BYTES +
@@ -217,7 +252,7 @@ poison_planes_kernel(unsigned char *planes, uint32_t dim, const uint64_t *rows, 
 {
     const uint32_t chunks = dim / 8;
     const uint64_t total = n * chunks;
-    const uint4 nan8 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);   // 8 x bf16 quiet NaN
+    const uint4 nan8 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);   // 0x7fc0 is a quiet NaN as bf16 AND as fp16
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t row = rows[i / chunks];
         if (row >= planes_rows) continue;              // not tiled yet: split_planes_kernel will read the NaN row of X
@@ -239,7 +274,9 @@ struct Params {
     uint32_t n_tiles;             // ceil(n_rows / 64)
     uint32_t parts;               // row partitions (gridDim.y)
     uint32_t dim;
-    uint32_t debug;               // timing experiments only: 1-3 give wrong results, 8 = no group early-out (correct); see the epilogue
+    uint32_t fmt;                 // FMT_BF16 / FMT_FP16: element format of the planes (and of the queries staged in TMEM)
+    uint32_t debug;               // 8 = no group early-out (correct results, A/B baseline); other values are timing probes
+                                  // that only exist in -DSEMA_K3_PROBES builds
 };
 
 // PASSES = 3: bf16x3 split (hi.hi + lo.hi + hi.lo), a stage holds the hi and lo plane blocks.
@@ -314,26 +351,37 @@ batch_scan_kernel(const Params p)
     constexpr uint16_t cmask = (uint16_t)((1u << C) - 1u);
     constexpr uint32_t SLICE = STAGE / C;
 
-    // ---- epilogue warps stage the query tile(s) into TMEM (A operand): row m <-> lane m
+    // ---- epilogue warps stage the query tile(s) into TMEM (A operand): row m <-> lane m.  Each query is scaled by a
+    // power of two so that its largest element lies in [0.5, 1) (exact; keeps any query inside fp16's range);
+    // the scores of its TMEM lane carry the same factor, and the published threshold is divided by it again.
+    float qscale0 = 1.0f, qscale1 = 1.0f;
     if (warp >= 2 && warp <= 5) {
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+        const int fmt = (int)p.fmt;
 #pragma unroll 1
         for (int qi = 0; qi < QT; ++qi) {
             const float *q = p.Q + (((size_t)qt * QT + qi) * TILE_Q + m) * p.dim;
+            float amax = 0.0f;
+            for (uint32_t c = 0; c < p.dim; c += 4) {
+                const float4 f = *reinterpret_cast<const float4 *>(q + c);
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y))), fmaxf(fabsf(f.z), fabsf(f.w)));
+            }
+            const float sc = query_scale(amax);
+            if (qi) qscale1 = sc; else qscale0 = sc;
             for (uint32_t c = 0; c < p.dim; c += 16) {
                 float v[16];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float4 f = *reinterpret_cast<const float4 *>(q + c + 4 * e);
-                    v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
+                    v[4 * e] = f.x * sc; v[4 * e + 1] = f.y * sc; v[4 * e + 2] = f.z * sc; v[4 * e + 3] = f.w * sc;
                 }
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    hi[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-                    lo[e] = pack_bf16(v[2 * e] - bf16_round(v[2 * e]), v[2 * e + 1] - bf16_round(v[2 * e + 1]));
+                    hi[e] = pack16(fmt, v[2 * e], v[2 * e + 1]);
+                    lo[e] = pack16(fmt, v[2 * e] - round16(fmt, v[2 * e]), v[2 * e + 1] - round16(fmt, v[2 * e + 1]));
                 }
                 tmem_st8(lane_addr + qi * acols + c / 2, hi);
                 if (PASSES == 3) tmem_st8(lane_addr + acols + c / 2, lo);
@@ -374,7 +422,7 @@ batch_scan_kernel(const Params p)
         // UMMAs (hi.hi, lo.hi, hi.lo) or 1 (single pass).  The warp stays converged so that
         // descriptors and TMEM addresses live in uniform registers. =====
         const uint32_t w = warp == 1 ? 0u : 1u;
-        constexpr uint32_t idesc = make_idesc();
+        const uint32_t idesc = make_idesc((int)p.fmt, TILE_Q, TILE_N);
         // Two issuers need the ring to hold two whole tiles when they work on different tiles
         // (an mbarrier waiter may be at most one phase ahead); otherwise issuer 0 works alone.
         const bool dual = QT == 2 || 2 * kblocks <= (uint32_t)STAGES;
@@ -445,7 +493,7 @@ batch_scan_kernel(const Params p)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);   // MMA may overwrite this accumulator
                 const uint32_t row0 = t * TILE_N;
-                if (p.debug == 1) continue;                       // probe: no scan at all
+                if (PROBES && p.debug == 1) continue;             // probe: no scan at all
                 // Pass 0: the maximum of each group of 16 scores (8 three-input maxima per group).  Once the
                 // lists have warmed up almost no group holds a score above the admission threshold, and a
                 // group nobody in the warp needs is skipped: the epilogue's instruction issue is energy the
@@ -473,7 +521,7 @@ batch_scan_kernel(const Params p)
                 const uint32_t live = p.n_rows - row0;           // rows of this tile that exist (>= 1)
                 if (live < 32) { mask[0] &= (1u << live) - 1u; mask[1] = 0u; }
                 else if (live < 64) mask[1] &= (1u << (live - 32)) - 1u;
-                if (p.debug == 2) { if (mask[0] | mask[1]) thr = fmaxf(thr, -1e30f); continue; }   // probe: mask pass only
+                if (PROBES && p.debug == 2) { if (mask[0] | mask[1]) thr = fmaxf(thr, -1e30f); continue; }   // probe: mask pass only
                 // Pass 2 (rare, not unrolled: keeps the instruction footprint small): insert them.
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -491,7 +539,7 @@ batch_scan_kernel(const Params p)
                         lsc[slot * TILE_Q + m] = v;
                         lrow[slot * TILE_Q + m] = row0 + h * 32 + c;
                         if (cnt < KC) ++cnt;
-                        if (p.debug == 3 && cnt == KC) { thr = fmaxf(thr, v * 0.5f); continue; }   // probe: no rescan
+                        if (PROBES && p.debug == 3 && cnt == KC) { thr = fmaxf(thr, v * 0.5f); continue; }   // probe: no rescan
                         if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
                             float mn = lsc[m];
                             int mp = 0;
@@ -518,7 +566,7 @@ batch_scan_kernel(const Params p)
             const size_t q = ((size_t)qt * QT + qi) * TILE_Q + m;
             uint32_t *out = p.cand_rows + (q * p.parts + part) * KC;
             for (int i = 0; i < KC; ++i) out[i] = i < cnt ? lrow[i * TILE_Q + m] : 0xffffffffu;
-            p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr : -INFINITY;
+            p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr / (qi ? qscale1 : qscale0) : -INFINITY;   // back to q's own scale (exact)
         }
     }
 
@@ -543,7 +591,8 @@ struct RescoreParams {
     uint32_t *flags;           // [nq] 1 = exactness not proven, re-run through K2
     uint32_t ld4, dim, k, parts, kc, row_base;
     const float *max_norm2;    // device: [max, min] squared row norm seen by K1 (bounds |x|)
-    float err_rel;             // |tensor-core score - exact score| <= err_rel * |q| * max|x|
+    float err_rel;             // |tensor-core score - exact score| <= err_rel * |q| * max|x| + err_abs * |q|
+    float err_abs;
 };
 // METRIC_L2: the tensor-core pass still selects by dot product (the planes hold x, the queries q);
 // the candidates are re-scored with K2's squared-L2 arithmetic and ranked by ascending distance.
@@ -594,12 +643,28 @@ rescore_kernel(const RescoreParams p)
         for (int j = 0; j < M; ++j)
             if (j == kj) kk = top.v[j];
         kk = __shfl_sync(FULL, kk, kl);
-        float qq = 0.0f;
-        for (uint32_t v = lane; v < nv; v += 32) qq = accum4<METRIC_COSINE>(qq, qp[v], qp[v]);
+        // |q|, computed on the query scaled into [0.5, 1) by a power of two so that |q|^2 can neither overflow nor
+        // vanish (the L2 proof below needs the plain |q|^2, which is as representable as the distances themselves)
+        float amax = 0.0f;
+        for (uint32_t v = lane; v < nv; v += 32) {
+            const float4 f = qp[v];
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y))), fmaxf(fabsf(f.z), fabsf(f.w)));
+        }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) qq += __shfl_xor_sync(FULL, qq, d);
+        for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, d));
+        const float qs = query_scale(amax);
+        float qq = 0.0f, qqs = 0.0f;
+        for (uint32_t v = lane; v < nv; v += 32) {
+            const float4 f = qp[v];
+            qq = accum4<METRIC_COSINE>(qq, f, f);
+            const float4 g = make_float4(f.x * qs, f.y * qs, f.z * qs, f.w * qs);
+            qqs = accum4<METRIC_COSINE>(qqs, g, g);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) { qq += __shfl_xor_sync(FULL, qq, d); qqs += __shfl_xor_sync(FULL, qqs, d); }
         if (lane == 0) {
-            const float err_bound = p.err_rel * sqrtf(qq) * sqrtf(p.max_norm2[0]);
+            const float qnorm = sqrtf(qqs) / qs;
+            const float err_bound = qnorm * (p.err_rel * sqrtf(p.max_norm2[0]) + p.err_abs);
             bool proven = true;
             if (worst > -INFINITY) {
                 if (METRIC == METRIC_L2)   // key_rank = -distance; slack for the fp32 evaluation of the bound itself

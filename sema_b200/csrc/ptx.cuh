@@ -40,6 +40,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
         : "memory");
 }
+// Wait on a barrier whose completing arrival may come from ANOTHER CTA of the cluster (remote mbarrier.arrive,
+// multicast tcgen05.commit).  No suspend-time hint: with the long hint above a waiter that is already asleep when the
+// remote arrival lands is not woken by it (measured: the CTA-pair K3 kernel ran 3x slower, ~0.7 us per stage, with
+// every remote-completed wait on the critical path), so this form re-polls at the hardware's own short limit.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SEMA_WAITC:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SEMA_DONEC;\n\t"
+        "bra SEMA_WAITC;\n\t"
+        "SEMA_DONEC:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// Pure polling wait (mbarrier.test_wait never suspends the thread): for barriers completed from outside the CTA when
+// every microsecond of wake-up latency is on the critical path.  backoff_ns > 0 sleeps between polls.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity, uint32_t backoff_ns = 0)
+{
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        if (backoff_ns) asm volatile("nanosleep.u32 %0;" ::"r"(backoff_ns));
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"

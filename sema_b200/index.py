@@ -227,6 +227,15 @@ class GpuIndex:
         """0 = automatic (K3 precision cascade), 1 = K2 once per query, 2 = K3 bf16x3, 3 = K3 single pass."""
         return self._L.sema_index_set_batch_mode(self._h, mode)
 
+    def set_batch_precision(self, prec: int) -> int:
+        """0 = automatic (fp16 halves when every stored element is <= 1024 in magnitude, else bf16), 1 = bf16 always."""
+        return self._L.sema_index_set_batch_precision(self._h, prec)
+
+    @property
+    def batch_precision_active(self) -> int:
+        """Format the K3 planes are in: 0 bf16, 1 fp16, -1 none built yet."""
+        return int(self._L.sema_index_batch_precision_active(self._h))
+
     def batch_stats(self) -> tuple[int, int]:
         """-> (queries served by K3, of which re-run through K2 for lack of an exactness proof)."""
         a, b = C.c_uint64(), C.c_uint64()

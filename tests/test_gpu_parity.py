@@ -399,18 +399,21 @@ K3_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", [2, 3], ids=["bf16x3", "bf16x1"])
+@pytest.mark.parametrize("prec", [0, 1], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("mode", [2, 3], ids=["x3", "x1"])
 @pytest.mark.parametrize("n,nq,k", K3_CASES)
-def test_k3_batch_matches_oracle_and_k2(sema, oracle_c, n, nq, k, mode):
+def test_k3_batch_matches_oracle_and_k2(sema, oracle_c, n, nq, k, mode, prec):
     d = 384
     X = _unit(1, n, d)
     Q = _unit(2, nq, d)
     with sema.GpuIndex(d, n) as idx:
         idx.append(X, normalize=False)
         assert idx.set_batch_mode(mode) == mode           # tensor-core path (3 passes / 1 pass)
+        assert idx.set_batch_precision(prec) == prec      # automatic -> fp16 halves on unit rows; 1 = bf16 halves
         ids3, sc3, nf3 = idx.search_batch(Q, k)
         served, fallbacks = idx.batch_stats()
         assert served == nq                                # K3 really ran
+        assert idx.batch_precision_active == (1 if prec == 0 else 0)
         idx.set_batch_mode(1)                              # K2 once per query
         ids2, sc2, nf2 = idx.search_batch(Q, k)
     assert np.array_equal(nf3, nf2) and (nf3 == min(k, n)).all()
@@ -443,6 +446,67 @@ def test_k3_ties_and_duplicates_fall_back_to_exact_path(sema, oracle_c):
     r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
     for i in range(8):
         O.check_parity(ids[i], sc[i], r_ids[i], r_sc[i])
+
+
+PAIR_CASES = [
+    # n, d, nq, k: the single-pass stage as CTA pairs (nq > 128: at least two query tiles).  Tile counts odd and
+    # even, a last tile of one row, dims from one k-block to the TMEM limit, every candidate-list size
+    (65, 384, 129, 10), (129, 384, 200, 10), (4160, 384, 256, 10), (4161, 64, 130, 16), (50001, 384, 300, 50),
+    (20000, 512, 257, 100), (9999, 128, 512, 10), (70000, 384, 1024, 10), (30000, 256, 384, 32),
+]
+
+
+@pytest.mark.parametrize("variant", [701, 700], ids=["pairs", "single-cta"])
+@pytest.mark.parametrize("n,d,nq,k", PAIR_CASES)
+def test_k3_pair_kernel_matches_oracle_and_k2(sema, oracle_c, n, d, nq, k, variant):
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        idx.set_batch_mode(3)
+        assert idx.set_scan_variant(variant) == variant
+        ids3, sc3, nf3 = idx.search_batch(Q, k)
+        served, fallbacks = idx.batch_stats()
+        assert served == nq
+        idx.set_batch_mode(1)
+        ids2, sc2, nf2 = idx.search_batch(Q, k)
+    assert np.array_equal(nf3, nf2) and (nf3 == min(k, n)).all()
+    assert np.array_equal(ids3, ids2) and np.array_equal(sc3, sc2)
+    r_ids, r_sc, _ = oracle_c.scan_batch(X, Q, k)
+    for i in range(0, nq, 7):
+        O.check_parity(ids3[i, :nf3[i]], sc3[i, :nf3[i]], r_ids[i, :nf3[i]], r_sc[i, :nf3[i]])
+    assert fallbacks <= max(1, nq // 50)                   # the pair kernel's lists prove ~all random queries
+
+
+@pytest.mark.parametrize("qmag,xmag,want_fmt", [(1e6, 1.0, 1), (1e-6, 1.0, 1), (3.0, 500.0, 1), (1.0, 5000.0, 0), (1e30, 1e-3, 1)])
+def test_k3_query_scaling_and_format_choice(sema, oracle_c, qmag, xmag, want_fmt):
+    """Queries of any magnitude are scaled by a power of two inside the kernel (fp16's range is narrow); rows
+    decide the format: fp16 halves while every element is <= 1024, bf16 beyond."""
+    n, d, nq, k = 20000, 384, 160, 10
+    X = (_unit(1, n, d) * np.float32(xmag)).astype(np.float32)
+    Q = (_unit(2, nq, d) * np.float32(qmag)).astype(np.float32)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        for mode in (3, 2, 0):
+            idx.set_batch_mode(mode)
+            q0, f0 = idx.batch_stats()
+            ids3, sc3, nf3 = idx.search_batch(Q, k)
+            q1, f1 = idx.batch_stats()
+            assert q1 - q0 == nq and f1 - f0 <= 3
+            assert idx.batch_precision_active == want_fmt
+            idx.set_batch_mode(1)
+            ids2, sc2, nf2 = idx.search_batch(Q, k)
+            assert np.array_equal(ids3, ids2) and np.array_equal(sc3, sc2) and (nf3 == k).all()
+    r_ids, r_sc, _ = oracle_c.scan_batch(X, Q[:16], k)
+    for i in range(16):
+        O.check_parity(ids3[i], sc3[i], r_ids[i], r_sc[i])
+
+
+def test_k3_probe_settings_are_refused_by_the_shipped_library(sema):
+    with sema.GpuIndex(384, 64) as idx:
+        for bad in (301, 302, 303, 316, 332, 364, 702, 800):
+            assert idx.set_scan_variant(bad) == -1
+        assert idx.set_scan_variant(308) == 308 and idx.set_scan_variant(300) == 300
 
 
 def test_k3_null_rows_appends_and_tombstones(sema, oracle_c):
@@ -788,7 +852,8 @@ def test_shard_group_with_an_empty_shard(sema):
             g.close()
 
 
-def test_k3_precision_cascade_in_automatic_mode(sema, oracle_c):
+@pytest.mark.parametrize("prec", [0, 1], ids=["fp16", "bf16"])
+def test_k3_precision_cascade_in_automatic_mode(sema, oracle_c, prec):
     """Automatic mode: single bf16 pass first; queries whose proof fails under its loose bound move to
     the bf16x3 stage; only what neither proves goes through K2.  Dense neighbourhood: 200 rows whose
     cosine to the query steps down by 1e-4 from 0.9 — the 10th and the 32nd candidate are 2.2e-3 apart
@@ -807,6 +872,7 @@ def test_k3_precision_cascade_in_automatic_mode(sema, oracle_c):
     X = O.normalize(X)
     with sema.GpuIndex(d, n) as idx:
         idx.append(X, normalize=False)
+        idx.set_batch_precision(prec)
         ids, sc, nf = idx.search_batch(Q, k)                  # automatic mode
         served, fallbacks = idx.batch_stats()
         cascaded = idx.batch_cascaded
@@ -824,7 +890,8 @@ def test_k3_precision_cascade_in_automatic_mode(sema, oracle_c):
     assert cascaded in (0, fallbacks) or fallbacks == 0
 
 
-def test_k3_cascade_uses_bf16x3_stage_for_many_dense_queries(sema, oracle_c):
+@pytest.mark.parametrize("prec", [0, 1], ids=["fp16", "bf16"])
+def test_k3_cascade_uses_bf16x3_stage_for_many_dense_queries(sema, oracle_c, prec):
     n, d, k = 30000, 384, 10
     rng = np.random.default_rng(8)
     X = _unit(1, n, d)
@@ -840,6 +907,7 @@ def test_k3_cascade_uses_bf16x3_stage_for_many_dense_queries(sema, oracle_c):
     X = O.normalize(X)
     with sema.GpuIndex(d, n) as idx:
         idx.append(X, normalize=False)
+        idx.set_batch_precision(prec)
         ids, sc, nf = idx.search_batch(Q, k)
         served, fallbacks = idx.batch_stats()
         cascaded = idx.batch_cascaded
