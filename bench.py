@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--nq", type=int, default=1024, help="queries per batch (--workload batch)")
     ap.add_argument("--batch-mode", type=int, default=2, help="0 auto (cascade), 1 K2 per query, 2 K3 three-pass split, 3 K3 single pass")
     ap.add_argument("--precision", type=int, default=0, help="K3 split format: 0 automatic (fp16 halves on unit-norm rows), 1 bf16 halves")
-    ap.add_argument("--k3-pair", type=int, default=-1, help="K3 single-pass stage: 0 single-CTA kernel, 1 CTA pairs (default) (tuning)")
+    ap.add_argument("--k3-pair", type=int, default=-1, help="K3 single-pass stage: 0 single-CTA kernel (default), 1 CTA pairs (tuning)")
     ap.add_argument("--k3-cluster", type=int, default=0, help="K3 cluster size (0 auto, 1, 2, 4) — tuning")
     ap.add_argument("--cpu-steps", type=int, default=10, help="timed whole-corpus CPU scans of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -400,6 +400,9 @@ def sub_single_1m(a, hc, dev, stream):
     return rec
 
 
+BATCH_IDLE_GAP_S = 0.4
+
+
 def batch_measure(idx, Qd, nq, k, mode, steps, stream):
     """One batched-search configuration on the tensor cores: -> (ms per batch, launches per batch, ids, scores, nf)."""
     import torch
@@ -412,7 +415,8 @@ def batch_measure(idx, Qd, nq, k, mode, steps, stream):
     for _ in range(3):
         idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     torch.cuda.synchronize()
-    l0 = idx.launch_count
+    time.sleep(BATCH_IDLE_GAP_S)      # the same short idle gap before every timed region: the board sits at its power cap
+    l0 = idx.launch_count             # under these kernels, and without it the previous mode's heat sets this one's clocks
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
@@ -466,7 +470,7 @@ def sub_batch(a, idx, hc, dev, stream, k2_ids, k2_sc):
            "metric": f"qps_batched_{nq}q_exact_top{k}_cosine_{a.rows}x{a.dim}_fp32", "modes": {}}
     # the three-pass split and the cascade in the default element format (fp16 halves on unit-norm rows), then the
     # three-pass split with bf16 halves (the north star's 3 x bf16 by name)
-    for prec, mode in ((0, 2), (0, 0), (1, 2)):
+    for prec, mode in ((0, 0), (0, 2), (1, 2)):
         idx.set_batch_precision(prec)
         q0, f0 = idx.batch_stats()
         c0 = idx.batch_cascaded
@@ -491,6 +495,8 @@ def sub_batch(a, idx, hc, dev, stream, k2_ids, k2_sc):
     idx.set_batch_mode(0)
     out["value"] = out["modes"]["cascade"]["value"]           # what sema_index_search_batch does by default
     out["value_is"] = "cascade (automatic mode, the call's default); the pure three-pass splits are listed beside it"
+    out["timing"] = (f"per mode: 3 warm-up batches, {BATCH_IDLE_GAP_S} s idle, then 6 batches back to back between two CUDA events on the "
+                     "launching stream")
     out["unit"] = "queries/s"
     out["verified"] = all(m["verified"] is not False for m in out["modes"].values())
     return out
@@ -827,6 +833,25 @@ def run_ours(a):
     qps = 1e3 / dev_ms
     e2e_qps = 1e3 / e2e_step_ms
 
+    # ---- N > 1: every rank's scan of its own shard WITHOUT the exchange (same stream of queries, local top-k only).
+    # The group runs at the pace of its slowest GPU; this shows how much of the gap to N x the 1-GPU rate is the
+    # spread between the N boards (the N = 1 run only ever measures GPU 0) and how much the exchange itself costs.
+    per_rank_local = None
+    if world > 1 and use_stream:
+        idx.search_stream_device(Qs.data_ptr(), a.warmup, k, ids_s.data_ptr(), sc_s.data_ptr(), nf_s.data_ptr())
+        loc = []
+        for _ in range(reps):
+            barrier()
+            e0.record(stream)
+            idx.search_stream_device(Qs.data_ptr(), a.steps, k, ids_s.data_ptr(), sc_s.data_ptr(), nf_s.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            loc.append(e0.elapsed_time(e1) / a.steps)
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = sorted(loc)[len(loc) // 2]
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank_local = [round(x, 6) for x in t.tolist()]
+
     # ---- every result of the timed stream must equal the pre-computed result of its pool query (query i =
     # pool[i % pool]): any race between chained launches, or between a launch and the peer exchange, breaks this
     stream_consistent = None
@@ -914,6 +939,10 @@ def run_ours(a):
                          if use_stream else "one search call per query",
                 "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks; "
                           f"the region of exactly {a.steps} steps is timed {reps} times, value = median",
+                "per_rank_local_scan_ms": per_rank_local,
+                "exchange_cost_ms_per_step": None if not per_rank_local else dev_ms - max(per_rank_local),
+                "per_rank_note": None if not per_rank_local else
+                    "ms per step of each rank's shard scan alone (no exchange, same query stream); the group cannot beat the slowest rank",
             },
             "repeats": {"device_ms_per_step": dev_spread, "e2e_ms_per_step": e2e_spread},
             "roofline": roof,
@@ -1064,7 +1093,7 @@ def run_batch(a):
         "unit": "queries/s", "n_gpus": 1, "steps": steps, "warmup": 3, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": rec["dtype"], "data": "synthetic",
         "config": {"workload": f"{a.rows}x{a.dim} fp32 corpus, batches of {nq} queries, exact top-{k} (BASELINE configs[2])",
-                   "batch_mode": rec["mode"], "k3_cluster": a.k3_cluster or "auto", "k3_pair": "default (CTA pairs)" if a.k3_pair < 0 else a.k3_pair,
+                   "batch_mode": rec["mode"], "k3_cluster": a.k3_cluster or "auto", "k3_pair": "default (single-CTA kernel)" if a.k3_pair < 0 else a.k3_pair,
                    "l2_flush": "none needed: each batch streams the 16-bit planes of the whole corpus"},
         "roofline": rec["roofline"], "batch": rec,
         "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * a.dim * 4,

@@ -27,7 +27,22 @@ def run(mode, variant, dbg, reps=4):
     for _ in range(reps): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     e1.record(stream); torch.cuda.synchronize()
     print(f"mode={mode} variant={variant} debug={dbg:2d}: {e0.elapsed_time(e1)/reps:.3f} ms", flush=True)
-for rnd in range(3):
-    for dbg in (0, 8, 2, 1, 17, 49):
-        run(3, 701, dbg, reps=3)
-    run(3, 700, 0, reps=3)
+import time, statistics
+def timed(mode, settings, reps=3):
+    for v in settings: assert idx.set_scan_variant(v) == v
+    idx.set_batch_mode(mode)
+    idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+    torch.cuda.synchronize(); time.sleep(0.4)                  # same short idle gap before every measurement
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+    e1.record(stream); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+cases = [("1pass c2", 3, [700, 102]), ("1pass c1", 3, [700, 101]), ("1pass c4", 3, [700, 104]), ("1pass pair", 3, [701, 100]),
+         ("3pass c4", 2, [700, 104]), ("3pass c2", 2, [700, 102]), ("3pass c1", 2, [700, 101])]
+res = {n: [] for n, _, _ in cases}
+for rnd in range(6):
+    for n, mode, st in (cases if rnd % 2 == 0 else cases[::-1]):
+        res[n].append(timed(mode, st))
+for n, v in res.items():
+    print(f"{n:12s} min {min(v):7.3f}  median {statistics.median(v):7.3f}  all {[round(x, 2) for x in v]}", flush=True)

@@ -72,6 +72,7 @@ int k3_choose_fmt(sema_index *s, int *fmt)
 // Bring the 16-bit planes up to date with rows [0, n).  Tombstones are poisoned in place (k3_poison_rows).
 int k3_sync_planes(sema_index *s, uint64_t n)
 {
+    SEMA_NVTX("sema.K3.split_planes");
     if (!s->planes || s->planes_rows < n || s->planes_prec != s->k3_prec) {   // new rows (or a new preference): (re)decide the format
         int fmt = k3::FMT_BF16;
         int rc = k3_choose_fmt(s, &fmt);
@@ -298,6 +299,7 @@ int k3_clusters(sema_index *s, int c, int *out)
 int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, int passes, uint64_t *ids_d,
              float *sc_d, uint32_t *nf_d)
 {
+    SEMA_NVTX("sema.K3.stage(scan+rescore)");
     // candidates kept per (query, row partition): the list minimum is the admission threshold and every
     // insertion re-scans the list, so the list is only as long as the exactness proof needs
     const uint32_t kc = (k <= 10 && passes == 1 && s->k3_kc16 != 0) ? 16 : (k <= 16 ? 32 : (k <= 48 ? 64 : 128));
@@ -314,9 +316,10 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
                       k3::pair_stages((int)kc, (int)s->dim) >= 2 * k3::pair_spt((int)s->dim);
     const int qt_per_cta = pair ? 1 : ((passes == 1 && q_tiles_all >= 2 && s->k3_qt != 1 && s->dim <= 384 && kc <= 64) ? 2 : 1);
     const uint32_t q_ctas_all = (q_tiles_all + qt_per_cta - 1) / qt_per_cta;
-    // measured on 10M x 384 x 1024q: bf16x3 is fastest with clusters of 4 (128 SMs, higher clocks under the
-    // power cap), the single-pass filter with clusters of 2 (144 SMs; it is bound by L2->SM delivery)
-    const int cpref = passes == 1 ? 2 : 4;
+    // measured on 10M x 384 x 1024q (alternating A/B, same idle gap before every measurement): clusters of 2 are
+    // fastest for both stages — single pass 5.64 ms (clusters of 4: 5.83, no cluster: 6.10), three passes 14.85 ms
+    // (clusters of 4: 15.29 on 132 of the 148 SMs, no cluster: 17.4)
+    const int cpref = 2;
     const int csize = pair ? 2
                            : (s->k3_cluster > 0 ? s->k3_cluster : (q_ctas_all >= (uint32_t)cpref ? cpref : (q_ctas_all >= 2 ? 2 : 1)));
     const uint32_t q_ctas_pad = ((q_ctas_all + csize - 1) / csize) * csize;
@@ -418,6 +421,7 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
 int k3_batch(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
              uint32_t *nf_d)
 {
+    SEMA_NVTX("sema.K3.batch");
     if (reinterpret_cast<uintptr_t>(Qd) & 15) {   // the kernels read queries as float4
         int rc0 = ensure(reinterpret_cast<void **>(&s->q_aligned), &s->q_aligned_cap, (size_t)nq * s->dim * sizeof(float));
         if (rc0) return rc0;
@@ -603,6 +607,7 @@ int sema_index_search_batch_keys_device(sema_index *s, const float *Q_dev, uint3
 int sema_topk_merge_batch_device(sema_index *s, const uint64_t *keys_dev, uint32_t n_lists, uint32_t nq, uint32_t k,
                                  uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
 {
+    SEMA_NVTX("sema.K4.merge_batch");
     if (!s || !keys_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
     if (k == 0 || nq == 0 || n_lists == 0) return fail(SEMA_ERR_INVALID, "k %u / nq %u / n_lists %u out of range", k, nq, n_lists);
     if (k > (uint32_t)K_PASS) return fail(SEMA_ERR_UNSUPPORTED, "the batched merge covers k <= %d", K_PASS);

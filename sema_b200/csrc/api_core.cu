@@ -87,6 +87,7 @@ namespace {
 int launch_ingest(sema_index *s, const float *src, uint64_t src_ld, uint64_t first, uint64_t n,
                   const uint8_t *valid_in, int normalize, bool vec4)
 {
+    SEMA_NVTX("sema.K1.ingest");
     float *dst = s->X + first * s->ld;
     const unsigned blocks = ingest_blocks(s, n);
     if (vec4)
@@ -381,6 +382,7 @@ int sema_index_append_synthetic(sema_index *s, uint64_t seed, uint64_t synth_row
 
 int sema_index_tombstone(sema_index *s, const uint64_t *rows, uint64_t n)
 {
+    SEMA_NVTX("sema.tombstone");
     if (!s) return fail(SEMA_ERR_INVALID, "null index");
     if (n && !rows) return fail(SEMA_ERR_INVALID, "null rows");
     if (n == 0) return SEMA_OK;
@@ -413,6 +415,7 @@ int sema_index_compact(sema_index *s, uint64_t *new_row_of_old, uint64_t *n_live
 
 int sema_index_compact_keep(sema_index *s, const uint8_t *keep, uint64_t *new_row_of_old, uint64_t *n_live_out)
 {
+    SEMA_NVTX("sema.compact");
     if (!s) return fail(SEMA_ERR_INVALID, "null index");
     int rc = sema_index_flush(s);
     if (rc) return rc;
@@ -660,7 +663,7 @@ int sema_index_set_scan_variant(sema_index *s, int variant)
 #endif
     if (variant >= 800) return -1;
     if (variant >= 702) return -1;
-    if (variant >= 700) { s->k3_pair = variant - 700; return variant; }      // 700 = single-CTA kernel for the single-pass stage, 701 = CTA pairs (default)
+    if (variant >= 700) { s->k3_pair = variant - 700; return variant; }      // 700 = single-CTA kernel for the single-pass stage (default), 701 = CTA pairs (tcgen05 cta_group::2)
     if (variant >= 600) { s->chain = variant - 600; return variant; }        // 600 / 601 = query streams unchained / chained (PDL)
     if (variant >= 500) { s->host_path = variant - 500; return variant; }    // 500 / 501 = host searches staged through H2D + D2H / query by kernel parameter + mapped results
     if (variant >= 400) { s->k3_kc16 = variant - 400; return variant; }      // 400 = lists of 32, 401 = lists of 16 (k <= 10, single pass)

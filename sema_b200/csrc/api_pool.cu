@@ -11,6 +11,7 @@ namespace sema_impl {
 int launch_pool(sema_index *s, cudaStream_t stream, const float *tokens_dev, const float *mask_dev, uint64_t n,
                 uint32_t seq_len, int skip_masked, float *out_dev, uint64_t out_ld)
 {
+    SEMA_NVTX("sema.K0.pool");
     const size_t smem = (3 * (size_t)seq_len + s->dim) * sizeof(float);
     if (smem > 200 * 1024) return fail(SEMA_ERR_UNSUPPORTED, "3 x seq_len %u + dim %u floats exceed shared memory", seq_len, s->dim);
     static bool attr_set[64] = {false};

@@ -205,6 +205,7 @@ int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64
                uint64_t *res_ids, float *res_scores, uint32_t *res_nfound, const Exchange *x, unsigned flags,
                uint64_t host_ticket)
 {
+    SEMA_NVTX("sema.K2.scan");
     if (k <= K_PASS) {
         ScanArgs a{q_dev, n, k, nullptr, out_keys ? out_keys : s->keys_dev, res_ids, res_scores, res_nfound, x, flags, host_ticket};
         return scan_pass(s, a);
@@ -235,6 +236,7 @@ bool host_query_ok(const sema_index *s, uint32_t k)
 // chaining is enabled.  Its own merge / exchange / result phase still waits for the predecessor.
 int host_query_launch(sema_index *s, const float *q_host, uint32_t n, uint32_t k, const Exchange *x, uint64_t ticket)
 {
+    SEMA_NVTX("sema.K2.scan(host query)");
     unsigned char *slot = s->res_map_dev + (ticket % RES_SLOTS) * RES_SLOT_BYTES;
     uint64_t *ids_m = reinterpret_cast<uint64_t *>(slot + 8);
     float *sc_m = reinterpret_cast<float *>(slot + 8 + 8 * (size_t)k);
@@ -446,6 +448,7 @@ int sema_index_search_device(sema_index *s, const float *q_dev, uint32_t k, uint
 int sema_topk_merge_device(sema_index *s, const uint64_t *keys_dev, uint32_t n_lists, uint32_t k,
                            uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev)
 {
+    SEMA_NVTX("sema.K4.merge");
     if (!s || !keys_dev || !ids_dev || !scores_dev || !n_found_dev) return fail(SEMA_ERR_INVALID, "null argument");
     if (k == 0 || k > SEMA_MAX_K) return fail(SEMA_ERR_INVALID, "k %u outside [1, %u]", k, SEMA_MAX_K);
     if ((uint64_t)n_lists * k > 0x7fffffffull) return fail(SEMA_ERR_INVALID, "too many candidates");

@@ -14,6 +14,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <deque>
 #include <exception>
 #include <new>
@@ -34,6 +36,18 @@ int fail(int code, const char *fmt, ...);   // sets the thread-local error text,
             return ::sema_impl::fail(SEMA_ERR_CUDA, "%s failed: %s (%s:%d)", #call,       \
                                      cudaGetErrorString(e_), __FILE__, __LINE__);         \
     } while (0)
+
+// NVTX range around every kernel-launching step (K0-K4, plane split, tombstones, compaction): a timeline tool
+// (nsys, ncu --nvtx) shows the path's phases by name; without a tool attached a push / pop is a null-pointer test.
+struct NvtxScope {
+    explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+    NvtxScope(const NvtxScope &) = delete;
+    NvtxScope &operator=(const NvtxScope &) = delete;
+};
+#define SEMA_NVTX_CAT2(a, b) a##b
+#define SEMA_NVTX_CAT(a, b) SEMA_NVTX_CAT2(a, b)
+#define SEMA_NVTX(name) ::sema_impl::NvtxScope SEMA_NVTX_CAT(nvtx_scope_, __LINE__)(name)
 
 struct Pending {
     cudaEvent_t ev;
@@ -120,7 +134,7 @@ struct sema_index {
     int k3_debug = 0;                   // timing experiments only (wrong results): see k3::Params::debug
     int k3_kc16 = 1;                    // single-pass stage with k <= 10 keeps 16 candidates per list (0 = 32) — tuning
     int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
-    int k3_pair = 1;                    // single-pass stage: 1 = CTA pairs (cta_group::2), 0 = the single-CTA kernel — tuning
+    int k3_pair = 0;                    // single-pass stage: 0 = the single-CTA kernel (two query tiles per CTA, clusters of 2: 5.64 ms on config 3), 1 = CTA pairs (cta_group::2: 6.22 ms) — tuning
     int k3_prec = 0;                    // plane format preference: 0 = automatic (fp16 when every |x_i| <= 1024, else bf16), 1 = bf16 always
     int planes_fmt = 0;                 // format the planes are in now (k3::FMT_BF16 / FMT_FP16)
     int planes_prec = 0;                // the preference they were built under

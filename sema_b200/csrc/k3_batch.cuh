@@ -27,8 +27,10 @@
 // MMA against the epilogue.  Each epilogue thread owns one query (= one TMEM lane): it
 // reads its 64 scores with tcgen05.ld and keeps a private candidate list in shared memory.
 //
-// Warp roles (224 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer 0,
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4), warp 6 = MMA issuer 1.
+// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer 0,
+// warps 2..5 = epilogue set 0 (TMEM lane quarter = warp % 4), warp 6 = MMA issuer 1, warps 7..10 = epilogue set 1
+// (two query tiles per CTA only: each set then drains one tile's accumulator, so a drain — tcgen05.ld of 32 KB,
+// mask pass, insertions: ~0.75 us — has two accumulator periods of MMA time to hide in instead of one).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -47,7 +49,7 @@ constexpr int BLOCK_K = 64;            // k elements per pipeline stage
 constexpr int UMMA_K = 16;             // k per tcgen05.mma (bf16)
 constexpr int STAGE_PLANE_BYTES = TILE_N * BLOCK_K * 2;   // 8 KB: one plane of one stage
 constexpr int STAGE_BYTES = 2 * STAGE_PLANE_BYTES;        // hi + lo = 16 KB
-constexpr int THREADS = 224;
+constexpr int THREADS = 352;            // 11 warps: see the roles at batch_scan_kernel
 constexpr int EPI_THREADS = 128;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_DIM = 384;           // bf16x3: q_hi + q_lo need dim TMEM columns; 128 are the accumulators
@@ -318,7 +320,10 @@ batch_scan_kernel(const Params p)
     uint64_t *acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, so the role branches below are uniform
+    // control flow and the MMA issue loop keeps descriptors / TMEM addresses in uniform registers (UIADD3 + UTCHMMA
+    // instead of ~15 instructions with four R2UR per MMA, which made one issuing warp slower than the tensor pipe)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t qt = blockIdx.x, part = blockIdx.y;   // this CTA's query tiles: qt*QT .. qt*QT + QT-1
     const uint32_t kblocks = p.dim / BLOCK_K;            // stages per tile
     const uint32_t acols = p.dim / 2;                    // TMEM columns per query plane
@@ -355,13 +360,15 @@ batch_scan_kernel(const Params p)
     // power of two so that its largest element lies in [0.5, 1) (exact; keeps any query inside fp16's range);
     // the scores of its TMEM lane carry the same factor, and the published threshold is divided by it again.
     float qscale0 = 1.0f, qscale1 = 1.0f;
-    if (warp >= 2 && warp <= 5) {
+    // epilogue set of this warp: 0 = warps 2..5, 1 = warps 7..10 (active with two query tiles per CTA), -1 = none
+    const int eset = (warp >= 2 && warp <= 5) ? 0 : ((QT == 2 && warp >= 7) ? 1 : -1);
+    if (eset >= 0) {
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
         const int fmt = (int)p.fmt;
 #pragma unroll 1
-        for (int qi = 0; qi < QT; ++qi) {
+        for (int qi = (QT == 2 ? eset : 0); qi < (QT == 2 ? eset + 1 : 1); ++qi) {   // each set stages (and later drains) its own tile
             const float *q = p.Q + (((size_t)qt * QT + qi) * TILE_Q + m) * p.dim;
             float amax = 0.0f;
             for (uint32_t c = 0; c < p.dim; c += 4) {
@@ -465,9 +472,9 @@ batch_scan_kernel(const Params p)
             }
         }
         __syncwarp();
-    } else {
-        // ===== epilogue: thread m owns query m of each of the CTA's query tiles; private candidate
-        // lists in shared memory =====
+    } else if (eset >= 0) {
+        // ===== epilogue: thread m owns query m of its set's query tile (QT = 2: set s <-> tile s <-> accumulator s;
+        // QT = 1: set 0 alone drains both accumulators alternately); private candidate lists in shared memory =====
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + acc_col;
@@ -476,7 +483,7 @@ batch_scan_kernel(const Params p)
         uint32_t it = 0;
         for (uint32_t t = t0; t < t1; ++t, ++it) {
 #pragma unroll 1
-            for (int qi = 0; qi < QT; ++qi) {
+            for (int qi = (QT == 2 ? eset : 0); qi < (QT == 2 ? eset + 1 : 1); ++qi) {
                 const uint32_t buf = QT == 1 ? (it & 1) : (uint32_t)qi;
                 const uint32_t use = QT == 1 ? (it >> 1) : it;
                 float thr = qi ? thr1 : thr0;
@@ -559,7 +566,7 @@ batch_scan_kernel(const Params p)
         }
         // publish this partition's candidates for the CTA's queries
 #pragma unroll 1
-        for (int qi = 0; qi < QT; ++qi) {
+        for (int qi = (QT == 2 ? eset : 0); qi < (QT == 2 ? eset + 1 : 1); ++qi) {
             const float thr = qi ? thr1 : thr0;
             const int cnt = qi ? cnt1 : cnt0;
             const uint32_t *lrow = list_row + qi * KC * TILE_Q;

@@ -144,7 +144,10 @@ pair_scan_kernel(const Params p, const __grid_constant__ CUtensorMap tmap)
     uint64_t *dummy = acc_free_peer + 2;            // probe builds: target of extra commits, never waited on
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dummy + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, so the role branches below are uniform
+    // control flow and the MMA issue loop keeps descriptors / TMEM addresses in uniform registers (UIADD3 + UTCHMMA
+    // instead of ~15 instructions with four R2UR per MMA, which made one issuing warp slower than the tensor pipe)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
     const uint32_t half = crank & 1u;                    // 0 = leader of the pair
     const uint32_t leader_rank = crank & ~1u;
@@ -214,9 +217,14 @@ pair_scan_kernel(const Params p, const __grid_constant__ CUtensorMap tmap)
             if (t >= p.n_tiles) t = p.n_tiles - 1;       // odd tile count: the peer re-reads the last tile, masked in the epilogue
             for (uint32_t j = 0; j < spt; ++j) {
                 PAIR_WAIT(&done[stage], phase ^ 1);            // the MMAs that read this stage's previous occupant have retired
+                if (PROBES && (p.debug & 32768)) {                      // probe: no loads at all (the MMAs read stale shared memory)
+                    if (half == 0 && lane == 0) mbar_arrive(&full[stage]);
+                    __syncwarp();
+                } else {
                 if (half == 0) mbar_expect_tx(&full[stage], 2 * stage_bytes);   // my copy + the peer's
                 tma_load_3d_pair(ring + stage * stage_bytes, &tmap, 0u, 0u, t * kblocks + j * kps,
                                  mapa_u32(&full[stage], leader_rank));
+                }
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
         }
@@ -250,6 +258,10 @@ pair_scan_kernel(const Params p, const __grid_constant__ CUtensorMap tmap)
                     for (uint32_t x = 0; x < ((p.debug >> 9) & 7u); ++x) umma_commit_pair_multicast(dummy, (uint16_t)3);
                     for (uint32_t x = 0; x < ((p.debug >> 12) & 7u); ++x) umma_commit_pair_local(dummy);
                 }
+                if (PROBES && (p.debug & 128)) {                       // probe (with 32: no MMAs to wait for): plain arrives instead of the commit
+                    if (lane == 0) { mbar_arrive(&done[st]); mbar_arrive_remote(&done[st], leader_rank + 1); }
+                    __syncwarp();
+                } else
                 umma_commit_pair_multicast(&done[st], (uint16_t)3);    // both CTAs: stage free (last stage: accumulator ready)
                 if (++st == nstages) { st = 0; ph ^= 1; }
             }
