@@ -38,11 +38,15 @@ def timed(mode, settings, reps=3):
     for _ in range(reps): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     e1.record(stream); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-cases = [("1pass c2", 3, [700, 102]), ("1pass c1", 3, [700, 101]), ("1pass c4", 3, [700, 104]), ("1pass pair", 3, [701, 100]),
-         ("3pass c4", 2, [700, 104]), ("3pass c2", 2, [700, 102]), ("3pass c1", 2, [700, 101])]
+D = 1000000
+cases = [("single full", 3, [700, 102, D + 0]), ("single no-scan", 3, [700, 102, D + 1]),
+         ("pair full", 3, [701, D + 0]), ("pair no-scan", 3, [701, D + 1]), ("pair no-ld", 3, [701, D + 17]),
+         ("pair MMA only (no TMA, no ld)", 3, [701, D + 32768 + 17]), ("pair flow only (no MMA, no ld)", 3, [701, D + 49]),
+         ("pair barriers only", 3, [701, D + 32768 + 49])]
 res = {n: [] for n, _, _ in cases}
-for rnd in range(6):
+for rnd in range(4):
     for n, mode, st in (cases if rnd % 2 == 0 else cases[::-1]):
         res[n].append(timed(mode, st))
+idx.set_scan_variant(D)
 for n, v in res.items():
-    print(f"{n:12s} min {min(v):7.3f}  median {statistics.median(v):7.3f}  all {[round(x, 2) for x in v]}", flush=True)
+    print(f"{n:32s} min {min(v):7.3f}  median {statistics.median(v):7.3f}  all {[round(x, 2) for x in v]}", flush=True)
