@@ -38,15 +38,12 @@ def timed(mode, settings, reps=3):
     for _ in range(reps): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     e1.record(stream); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-D = 1000000
-cases = [("single full", 3, [700, 102, D + 0]), ("single no-scan", 3, [700, 102, D + 1]),
-         ("pair full", 3, [701, D + 0]), ("pair no-scan", 3, [701, D + 1]), ("pair no-ld", 3, [701, D + 17]),
-         ("pair MMA only (no TMA, no ld)", 3, [701, D + 32768 + 17]), ("pair flow only (no MMA, no ld)", 3, [701, D + 49]),
-         ("pair barriers only", 3, [701, D + 32768 + 49])]
+cases = [("1pass pf 0", 3, [700, 102, 800]), ("1pass pf 12", 3, [700, 102, 812]), ("1pass pf 24", 3, [700, 102, 824]), ("1pass pf 48", 3, [700, 102, 848]),
+         ("1pass pf 96", 3, [700, 102, 896]), ("1pass pf 192", 3, [700, 102, 992]),
+         ("3pass pf 0", 2, [700, 102, 800]), ("3pass pf 12", 2, [700, 102, 812]), ("3pass pf 24", 2, [700, 102, 824]), ("3pass pf 48", 2, [700, 102, 848])]
 res = {n: [] for n, _, _ in cases}
 for rnd in range(4):
     for n, mode, st in (cases if rnd % 2 == 0 else cases[::-1]):
         res[n].append(timed(mode, st))
-idx.set_scan_variant(D)
 for n, v in res.items():
     print(f"{n:32s} min {min(v):7.3f}  median {statistics.median(v):7.3f}  all {[round(x, 2) for x in v]}", flush=True)

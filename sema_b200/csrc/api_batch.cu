@@ -367,6 +367,7 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         p.parts = parts;
         p.dim = s->dim;
         p.fmt = (uint32_t)s->planes_fmt;
+        p.prefetch = (uint32_t)s->k3_prefetch;
         p.debug = (uint32_t)s->k3_debug;
         if (pair)
             rc = kc == 16 ? k3_launch_pair<16>(s, p, q_ctas) : kc == 32 ? k3_launch_pair<32>(s, p, q_ctas) : k3_launch_pair<64>(s, p, q_ctas);

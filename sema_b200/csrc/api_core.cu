@@ -661,7 +661,8 @@ int sema_index_set_scan_variant(sema_index *s, int variant)
 #ifdef SEMA_K3_PROBES
     if (variant >= 1000000) { s->k3_debug = variant - 1000000; return variant; }   // probe builds: wide probe masks
 #endif
-    if (variant >= 800) return -1;
+    if (variant >= 1000) return -1;
+    if (variant >= 800) { s->k3_prefetch = variant - 800; return variant; }  // 800 + d = K3 producer prefetches into L2 d stages ahead (0 = off)
     if (variant >= 702) return -1;
     if (variant >= 700) { s->k3_pair = variant - 700; return variant; }      // 700 = single-CTA kernel for the single-pass stage (default), 701 = CTA pairs (tcgen05 cta_group::2)
     if (variant >= 600) { s->chain = variant - 600; return variant; }        // 600 / 601 = query streams unchained / chained (PDL)

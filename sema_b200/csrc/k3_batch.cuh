@@ -91,6 +91,13 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t *bar, uint16_t ct
                  ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
+// pull `bytes` (a multiple of 16) at `src` into L2 without a destination in shared memory
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e cp.async.bulk.prefetch.L2.global [%0], %1;\n\t}" ::"l"(src), "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;
@@ -277,6 +284,7 @@ struct Params {
     uint32_t parts;               // row partitions (gridDim.y)
     uint32_t dim;
     uint32_t fmt;                 // FMT_BF16 / FMT_FP16: element format of the planes (and of the queries staged in TMEM)
+    uint32_t prefetch;            // L2 prefetch distance of the producer, in pipeline stages (0 = none)
     uint32_t debug;               // 8 = no group early-out (correct results, A/B baseline); other values are timing probes
                                   // that only exist in -DSEMA_K3_PROBES builds
 };
@@ -405,9 +413,20 @@ batch_scan_kernel(const Params p)
         // lane issues) =====
         {
             uint32_t stage = 0, phase = 0;
+            // L2 prefetch `p.prefetch` stages ahead of the copies: the shared-memory ring bounds the bytes in flight
+            // to the SM (192 KB), which at DRAM latency caps the operand stream below what the tensor pipe eats; a
+            // prefetch pulls the lines into L2 early without occupying a stage, so the real copy is an L2 hit
+            const uint32_t pf = p.prefetch;
+            const uint32_t pf_tiles = pf / kblocks, pf_kb = pf % kblocks;
             for (uint32_t t = t0; t < t1; ++t) {
                 const unsigned char *src = p.planes + (size_t)t * tile_bytes((int)p.dim);
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
+                    if (pf) {
+                        uint32_t tp = t + pf_tiles, kp = kb + pf_kb;
+                        if (kp >= kblocks) { kp -= kblocks; ++tp; }
+                        if (tp < t1)
+                            bulk_prefetch_l2(p.planes + (size_t)tp * tile_bytes((int)p.dim) + (size_t)kp * STAGE_BYTES + crank * SLICE, SLICE);
+                    }
                     mbar_wait(&empty[stage], phase ^ 1);     // all C consumers released this stage
                     mbar_expect_tx(&full[stage], STAGE);
                     // the planes hold [hi | lo] per k-block; a 1-pass stage fetches the hi half only
