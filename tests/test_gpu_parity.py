@@ -549,6 +549,62 @@ def test_k3_null_rows_appends_and_tombstones(sema, oracle_c):
         assert idx.batch_stats()[0] == 128
 
 
+@pytest.mark.parametrize("growable", [False, True], ids=["fixed", "growable"])
+@pytest.mark.parametrize("variant", [700, 701], ids=["single-cta", "pairs"])
+def test_k3_single_pass_kernels_follow_appends_and_tombstones(sema, oracle_c, variant, growable):
+    """Both single-pass kernels (the pair form reads the planes through a tensor map encoded once per planes
+    allocation, also for the growable index whose planes are an address-space reservation) must see later appends,
+    the re-tiled partial last tile, and rows poisoned in place by tombstones."""
+    n, d, k, nq = 40000, 384, 10, 200
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    cap = 2_000_000 if growable else n
+    with sema.GpuIndex(d, cap, growable=growable) as idx:
+        idx.set_batch_mode(3)
+        assert idx.set_scan_variant(variant) == variant
+        idx.append(X[:15001], normalize=False)                      # 235 tiles: odd, the last one holds 25 rows
+        ids, sc, nf = idx.search_batch(Q, k)
+        r = oracle_c.scan_batch(X[:15001], Q, k)
+        for i in range(0, nq, 5):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+        idx.append(X[15001:], normalize=False)
+        ids, sc, nf = idx.search_batch(Q, k)
+        r = oracle_c.scan_batch(X, Q, k)
+        for i in range(0, nq, 5):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+        dead = np.unique(ids[:, :2])                                # every query loses its two best rows
+        idx.tombstone(dead)
+        valid = np.ones(n, np.uint8)
+        valid[dead] = 0
+        ids, sc, nf = idx.search_batch(Q, k)
+        r = oracle_c.scan_batch(X, Q, k, valid=valid)
+        for i in range(0, nq, 5):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+        assert not np.isin(ids, dead).any()
+        served, fallbacks = idx.batch_stats()
+        assert served == 3 * nq and fallbacks <= 6
+
+
+def test_k3_prefetch_knob_does_not_change_results(sema, oracle_c):
+    n, d, k, nq = 30000, 384, 10, 150
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        out = []
+        for mode in (3, 2):
+            idx.set_batch_mode(mode)
+            for pf in (800, 807, 840):
+                assert idx.set_scan_variant(pf) == pf
+                out.append(idx.search_batch(Q, k))
+        idx.set_scan_variant(800)
+    for ids, sc, nf in out[1:]:
+        assert np.array_equal(ids, out[0][0]) and np.array_equal(sc, out[0][1])
+    r = oracle_c.scan_batch(X, Q[:8], k)
+    for i in range(8):
+        O.check_parity(out[0][0][i], out[0][1][i], r[0][i], r[1][i])
+
+
 def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
     # dim 1024 is served by K2 (one pass per query); the L2 metric over unit rows by K3: same results
     X = _unit(1, 5000, 1024)
