@@ -21,7 +21,7 @@ sc_d = torch.zeros(k, dtype=torch.float32, device=dev)
 nf_d = torch.zeros(1, dtype=torch.int32, device=dev)
 stream = torch.cuda.current_stream()
 out = []
-for rows in [1000, 10_000, 100_000, 250_000, 500_000, 1_000_000, 2_000_000, 5_000_000, 10_000_000]:
+for rows in [int(r) for r in os.environ.get("ROWS", "1000,10000,100000,250000,500000,1000000,2000000,5000000,10000000").split(",")]:
     idx = sema_b200.GpuIndex(384, rows)
     idx.append_synthetic(1, 0, rows, True)
     idx.set_stream(stream.cuda_stream)

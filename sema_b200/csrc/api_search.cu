@@ -75,17 +75,17 @@ int run_scan(sema_index *s, const ScanArgs &a)
 // rows reach the SM through a TMA bulk-copy ring (k2_scan_tma.cuh): the default for dim 384 / 768.
 // QP: the query travels as a kernel parameter (a.q_dev is then a HOST pointer to dim floats) and the
 // results / completion flag go to the handle's mapped host buffer.
-template <int NV, int M, int METRIC, bool QP>
-int run_scan_tma(sema_index *s, const ScanArgs &a)
+template <int NV, int M, int METRIC, bool QP, int CW>
+int run_scan_tma_cw(sema_index *s, const ScanArgs &a)
 {
-    auto kern = scan_topk_tma_kernel<NV, M, METRIC, QP>;
+    auto kern = scan_topk_tma_kernel<NV, M, METRIC, QP, CW>;
     static bool attr_set[64] = {false};
     if (!attr_set[s->device & 63]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes<NV>()));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tma_smem_bytes<NV, CW>()));
         attr_set[s->device & 63] = true;
     }
-    const uint32_t n_tiles = (a.n + tma_tile_rows<NV>() - 1) / tma_tile_rows<NV>();
-    uint32_t grid = (uint32_t)s->num_sms;
+    const uint32_t n_tiles = (a.n + tma_tile_rows<NV, CW>() - 1) / tma_tile_rows<NV, CW>();
+    uint32_t grid = (uint32_t)s->num_sms * (CW == 8 ? 1u : 2u);
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     ScanParams p;
@@ -104,8 +104,8 @@ int run_scan_tma(sema_index *s, const ScanArgs &a)
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(TMA_THREADS);
-    cfg.dynamicSmemBytes = tma_smem_bytes<NV>();
+    cfg.blockDim = dim3(tma_threads<CW>());
+    cfg.dynamicSmemBytes = tma_smem_bytes<NV, CW>();
     cfg.stream = s->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -117,6 +117,13 @@ int run_scan_tma(sema_index *s, const ScanArgs &a)
     CK(cudaLaunchKernelEx(&cfg, kern, p, qa));
     s->launches++;
     return SEMA_OK;
+}
+
+// variant 4 = two CTAs per SM (4 consumer warps, 24 KB stages each); default / 0 = one CTA per SM (8 warps, 48 KB stages)
+template <int NV, int M, int METRIC, bool QP>
+int run_scan_tma(sema_index *s, const ScanArgs &a)
+{
+    return s->variant == 4 ? run_scan_tma_cw<NV, M, METRIC, QP, 4>(s, a) : run_scan_tma_cw<NV, M, METRIC, QP, 8>(s, a);
 }
 
 template <int NV, int METRIC>
@@ -226,7 +233,7 @@ int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64
 bool host_query_ok(const sema_index *s, uint32_t k)
 {
     const uint32_t ld4 = s->ld / 4;
-    return s->host_path && s->variant == 0 && k >= 1 && k <= (uint32_t)K_PASS &&
+    return s->host_path && (s->variant == 0 || s->variant == 4) && k >= 1 && k <= (uint32_t)K_PASS &&
            s->ld == s->dim && (ld4 == 96 || ld4 == 192) && s->res_map != nullptr;
 }
 

@@ -15,17 +15,21 @@
 
 namespace sema {
 
-constexpr int TMA_CONSUMER_WARPS = 8;
-constexpr int TMA_THREADS = (TMA_CONSUMER_WARPS + 1) * 32;
 constexpr int TMA_STAGES = 4;
 
-// rows per tile: a stage is 48 KB for dim 384 (32 rows) and for dim 768 (16 rows)
-template <int NV>
-__host__ __device__ constexpr int tma_tile_rows() { return NV <= 3 ? 32 : 16; }
-template <int NV>
-__host__ __device__ constexpr int tma_stage_bytes() { return tma_tile_rows<NV>() * NV * 32 * 16; }
-template <int NV>
-__host__ __device__ constexpr int tma_smem_bytes() { return TMA_STAGES * tma_stage_bytes<NV>() + 256; }
+// CW = consumer warps per CTA.  CW = 8: one CTA per SM, stages of 48 KB (32 rows at dim 384, 16 at dim 768), 192 KB
+// in flight.  CW = 4: TWO CTAs per SM with stages of 24 KB each (the same 192 KB in flight per SM): when launches
+// follow each other in a query stream, a block of the next launch becomes resident as soon as ONE of the SM's two
+// blocks has merged and exited, so an SM is never entirely idle between launches (each launch's ramp and per-block
+// merge used to idle its SM for ~5 us: 2.5 % of a 0.26 ms shard scan).
+template <int CW>
+__host__ __device__ constexpr int tma_threads() { return (CW + 1) * 32; }
+template <int NV, int CW>
+__host__ __device__ constexpr int tma_tile_rows() { return (NV <= 3 ? 4 : 2) * CW; }   // rows per warp and tile: 4 (dim 384) / 2 (dim 768)
+template <int NV, int CW>
+__host__ __device__ constexpr int tma_stage_bytes() { return tma_tile_rows<NV, CW>() * NV * 32 * 16; }
+template <int NV, int CW>
+__host__ __device__ constexpr int tma_smem_bytes() { return TMA_STAGES * tma_stage_bytes<NV, CW>() + 256; }
 
 // The query itself as a kernel parameter (host-query entry points): it travels with the launch,
 // no H2D copy precedes the kernel.  QueryArg<0> is the placeholder of the device-pointer variant.
@@ -49,14 +53,15 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 // the producer's arrive.expect_tx; TMA_NO_TILE marks the end.  With back-to-back launches chained
 // by programmatic dependent launch, a block that starts late (its SM was still running the
 // predecessor's last-block merge / shard exchange) simply claims fewer tiles.
-template <int NV, int M, int METRIC, bool QP>
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+template <int NV, int M, int METRIC, bool QP, int CW>
+__global__ void __launch_bounds__(tma_threads<CW>(), CW == 8 ? 1 : 2)
 scan_topk_tma_kernel(const __grid_constant__ ScanParams p, const __grid_constant__ QueryArg<QP ? NV : 0> qa)
 {
     using namespace ptx;
-    constexpr int TMA_TILE_ROWS = tma_tile_rows<NV>();
+    constexpr int TMA_CONSUMER_WARPS = CW;
+    constexpr int TMA_TILE_ROWS = tma_tile_rows<NV, CW>();
     constexpr int R = TMA_TILE_ROWS / TMA_CONSUMER_WARPS;   // rows per warp and tile (4 or 2)
-    constexpr int STAGE = tma_stage_bytes<NV>();
+    constexpr int STAGE = tma_stage_bytes<NV, CW>();
     extern __shared__ __align__(128) unsigned char tsm[];
     uint64_t *full = reinterpret_cast<uint64_t *>(tsm + TMA_STAGES * STAGE);
     uint64_t *empty = full + TMA_STAGES;
