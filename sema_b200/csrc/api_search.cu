@@ -119,11 +119,13 @@ int run_scan_tma_cw(sema_index *s, const ScanArgs &a)
     return SEMA_OK;
 }
 
-// variant 4 = two CTAs per SM (4 consumer warps, 24 KB stages each); default / 0 = one CTA per SM (8 warps, 48 KB stages)
+// Two other shapes of the same kernel were measured and dropped (the template still takes them): CW = 4 (two CTAs per
+// SM, 24 KB stages: 7.35 TB/s against 7.61 at 10 M rows — smaller copies) and CW = 9 (two CTAs per SM, two 48 KB stages
+// each: equal at 1 M rows, slower below) — letting a successor launch's block move in early does not shorten a stream.
 template <int NV, int M, int METRIC, bool QP>
 int run_scan_tma(sema_index *s, const ScanArgs &a)
 {
-    return s->variant == 4 ? run_scan_tma_cw<NV, M, METRIC, QP, 4>(s, a) : run_scan_tma_cw<NV, M, METRIC, QP, 8>(s, a);
+    return run_scan_tma_cw<NV, M, METRIC, QP, 8>(s, a);
 }
 
 template <int NV, int METRIC>
@@ -233,7 +235,7 @@ int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64
 bool host_query_ok(const sema_index *s, uint32_t k)
 {
     const uint32_t ld4 = s->ld / 4;
-    return s->host_path && (s->variant == 0 || s->variant == 4) && k >= 1 && k <= (uint32_t)K_PASS &&
+    return s->host_path && s->variant == 0 && k >= 1 && k <= (uint32_t)K_PASS &&
            s->ld == s->dim && (ld4 == 96 || ld4 == 192) && s->res_map != nullptr;
 }
 

@@ -15,21 +15,25 @@
 
 namespace sema {
 
-constexpr int TMA_STAGES = 4;
-
 // CW = consumer warps per CTA.  CW = 8: one CTA per SM, stages of 48 KB (32 rows at dim 384, 16 at dim 768), 192 KB
 // in flight.  CW = 4: TWO CTAs per SM with stages of 24 KB each (the same 192 KB in flight per SM): when launches
 // follow each other in a query stream, a block of the next launch becomes resident as soon as ONE of the SM's two
 // blocks has merged and exited, so an SM is never entirely idle between launches (each launch's ramp and per-block
 // merge used to idle its SM for ~5 us: 2.5 % of a 0.26 ms shard scan).
+// CW = 9 is the third shape: 8 consumer warps and 48 KB stages like CW = 8, but only TWO stages per CTA and two CTAs per
+// SM (the same 4 x 48 KB in flight per SM, and a successor launch's block can move in when one of the two exits).
 template <int CW>
-__host__ __device__ constexpr int tma_threads() { return (CW + 1) * 32; }
+__host__ __device__ constexpr int tma_warps() { return CW == 9 ? 8 : CW; }
+template <int CW>
+__host__ __device__ constexpr int tma_stages() { return CW == 9 ? 2 : 4; }
+template <int CW>
+__host__ __device__ constexpr int tma_threads() { return (tma_warps<CW>() + 1) * 32; }
 template <int NV, int CW>
-__host__ __device__ constexpr int tma_tile_rows() { return (NV <= 3 ? 4 : 2) * CW; }   // rows per warp and tile: 4 (dim 384) / 2 (dim 768)
+__host__ __device__ constexpr int tma_tile_rows() { return (NV <= 3 ? 4 : 2) * tma_warps<CW>(); }   // rows per warp and tile: 4 (dim 384) / 2 (dim 768)
 template <int NV, int CW>
 __host__ __device__ constexpr int tma_stage_bytes() { return tma_tile_rows<NV, CW>() * NV * 32 * 16; }
 template <int NV, int CW>
-__host__ __device__ constexpr int tma_smem_bytes() { return TMA_STAGES * tma_stage_bytes<NV, CW>() + 256; }
+__host__ __device__ constexpr int tma_smem_bytes() { return tma_stages<CW>() * tma_stage_bytes<NV, CW>() + 256; }
 
 // The query itself as a kernel parameter (host-query entry points): it travels with the launch,
 // no H2D copy precedes the kernel.  QueryArg<0> is the placeholder of the device-pointer variant.
@@ -58,7 +62,8 @@ __global__ void __launch_bounds__(tma_threads<CW>(), CW == 8 ? 1 : 2)
 scan_topk_tma_kernel(const __grid_constant__ ScanParams p, const __grid_constant__ QueryArg<QP ? NV : 0> qa)
 {
     using namespace ptx;
-    constexpr int TMA_CONSUMER_WARPS = CW;
+    constexpr int TMA_CONSUMER_WARPS = tma_warps<CW>();
+    constexpr int TMA_STAGES = tma_stages<CW>();
     constexpr int TMA_TILE_ROWS = tma_tile_rows<NV, CW>();
     constexpr int R = TMA_TILE_ROWS / TMA_CONSUMER_WARPS;   // rows per warp and tile (4 or 2)
     constexpr int STAGE = tma_stage_bytes<NV, CW>();

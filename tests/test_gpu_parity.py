@@ -108,7 +108,7 @@ def test_k2_search_matches_oracle(sema, oracle_c, n, d, k, metric):
             assert np.all(np.diff(sc) >= 0) if metric else np.all(np.diff(sc) <= 0)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_k2_variants_agree(sema, oracle_c, variant):
     n, d = 30011, 384
     X = _unit(3, n, d)
