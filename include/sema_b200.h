@@ -310,9 +310,12 @@ int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float 
  * 200 / 201 = K3 two / one query tiles per CTA in the single-CTA single-pass kernel; 300 / 308 = K3 epilogue
  * with / without its group early-out; 400 / 401 = K3 single-pass candidate lists of 32 / 16 for k <= 10;
  * 500 / 501 = host searches staged through H2D + D2H copies / query by kernel parameter + results to mapped
- * host memory (default); 600 / 601 = query streams unchained / chained (default); 700 / 701 / 702 = K3
- * single-pass stage on the single-CTA kernel / on CTA pairs (tcgen05 cta_group::2, default) / on clusters of two
- * pairs with multicast; negative = query.  Returns the value set, or -1 for a value this build does not have. */
+ * host memory (default); 600 / 601 = query streams unchained / chained (default); 700 / 701 = K3 single-pass
+ * stage on the single-CTA kernel (default) / on CTA pairs (tcgen05 cta_group::2); 800 + d = K3 producer
+ * prefetches into L2 d stages ahead (default 0: measured no gain); 1100 / 1101 = a K3 stage as one launch / as
+ * two concurrent launches, clusters of 4 plus clusters of 2 on the SMs those leave free (default); 1200 + w = row
+ * weight of a 4-cluster partition in that split, percent above 1 (0 = built-in 1.05); negative = query.
+ * Returns the value set, or -1 for a value this build does not have. */
 int sema_index_set_scan_variant(sema_index *idx, int variant);
 /* number of kernels this handle has launched so far */
 uint64_t sema_index_launch_count(const sema_index *idx);

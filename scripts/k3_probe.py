@@ -38,9 +38,8 @@ def timed(mode, settings, reps=3):
     for _ in range(reps): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     e1.record(stream); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-cases = [("1pass pf 0", 3, [700, 102, 800]), ("1pass pf 12", 3, [700, 102, 812]), ("1pass pf 24", 3, [700, 102, 824]), ("1pass pf 48", 3, [700, 102, 848]),
-         ("1pass pf 96", 3, [700, 102, 896]), ("1pass pf 192", 3, [700, 102, 992]),
-         ("3pass pf 0", 2, [700, 102, 800]), ("3pass pf 12", 2, [700, 102, 812]), ("3pass pf 24", 2, [700, 102, 824]), ("3pass pf 48", 2, [700, 102, 848])]
+cases = [("1pass one launch", 3, [700, 100, 1100])] + [(f"1pass mixed w=1.{w:02d}", 3, [700, 100, 1101, 1200 + w]) for w in (1, 5, 9, 14, 20)] + \
+        [("3pass one launch", 2, [700, 100, 1100])] + [(f"3pass mixed w=1.{w:02d}", 2, [700, 100, 1101, 1200 + w]) for w in (1, 5, 9, 14, 20)]
 res = {n: [] for n, _, _ in cases}
 for rnd in range(4):
     for n, mode, st in (cases if rnd % 2 == 0 else cases[::-1]):

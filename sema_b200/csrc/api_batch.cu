@@ -121,7 +121,7 @@ int k3_sync_planes(sema_index *s, uint64_t n)
 
 // q_ctas = CTAs along the query axis (each owns QT query tiles)
 template <int KC, int C, int PASSES, int QT>
-int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_ctas)
+int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_ctas, uint32_t grid_parts, cudaStream_t stream)
 {
     auto kern = k3::batch_scan_kernel<KC, C, PASSES, QT>;
     static bool attr_set[64] = {false};
@@ -130,10 +130,10 @@ int k3_launch_scan_c(sema_index *s, const k3::Params &p, uint32_t q_ctas)
         attr_set[s->device & 63] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(q_ctas, p.parts, 1);
+    cfg.gridDim = dim3(q_ctas, grid_parts, 1);
     cfg.blockDim = dim3(k3::THREADS, 1, 1);
     cfg.dynamicSmemBytes = k3::Smem<KC, PASSES, QT>::TOTAL;
-    cfg.stream = s->stream;
+    cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C;
@@ -229,7 +229,7 @@ int k3_launch_pair(sema_index *s, const k3::Params &p, uint32_t q_tiles)
         attr_set[s->device & 63] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(q_tiles, p.parts, 1);
+    cfg.gridDim = dim3(q_tiles, p.parts, 1);      // the pair kernel always runs a stage as ONE launch: grid.y = all partitions
     cfg.blockDim = dim3(k3::PAIR_THREADS, 1, 1);
     cfg.dynamicSmemBytes = (size_t)k3_pair_smem(KC, p.dim);
     cfg.stream = s->stream;
@@ -272,24 +272,40 @@ int k3_pair_clusters(sema_index *s, int *out)
 }
 
 template <int KC, int PASSES, int QT>
-int k3_launch_scan_p(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c)
+int k3_launch_scan_p(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c, uint32_t grid_parts, cudaStream_t stream)
 {
-    return c == 4 ? k3_launch_scan_c<KC, 4, PASSES, QT>(s, p, q_ctas)
-         : c == 2 ? k3_launch_scan_c<KC, 2, PASSES, QT>(s, p, q_ctas) : k3_launch_scan_c<KC, 1, PASSES, QT>(s, p, q_ctas);
+    return c == 4 ? k3_launch_scan_c<KC, 4, PASSES, QT>(s, p, q_ctas, grid_parts, stream)
+         : c == 2 ? k3_launch_scan_c<KC, 2, PASSES, QT>(s, p, q_ctas, grid_parts, stream)
+                  : k3_launch_scan_c<KC, 1, PASSES, QT>(s, p, q_ctas, grid_parts, stream);
 }
 template <int KC>
-int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c, int passes, int qt)
+int k3_launch_scan(sema_index *s, const k3::Params &p, uint32_t q_ctas, int c, int passes, int qt, uint32_t grid_parts,
+                   cudaStream_t stream)
 {
-    if (passes == 3) return k3_launch_scan_p<KC, 3, 1>(s, p, q_ctas, c);
+    if (passes == 3) return k3_launch_scan_p<KC, 3, 1>(s, p, q_ctas, c, grid_parts, stream);
     if constexpr (KC <= 64) {
-        if (qt == 2) return k3_launch_scan_p<KC, 1, 2>(s, p, q_ctas, c);
+        if (qt == 2) return k3_launch_scan_p<KC, 1, 2>(s, p, q_ctas, c, grid_parts, stream);
     }
-    return k3_launch_scan_p<KC, 1, 1>(s, p, q_ctas, c);
+    return k3_launch_scan_p<KC, 1, 1>(s, p, q_ctas, c, grid_parts, stream);
 }
+int k3_launch_scan_kc(sema_index *s, uint32_t kc, const k3::Params &p, uint32_t q_ctas, int c, int passes, int qt,
+                      uint32_t grid_parts, cudaStream_t stream)
+{
+    return kc == 16 ? k3_launch_scan<16>(s, p, q_ctas, c, passes, qt, grid_parts, stream)
+         : kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, c, passes, qt, grid_parts, stream)
+         : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, c, passes, qt, grid_parts, stream)
+                    : k3_launch_scan<128>(s, p, q_ctas, c, passes, qt, grid_parts, stream);
+}
+int k3_clusters_kc(sema_index *s, uint32_t kc, int c, int *out);   // below
 template <int KC>
 int k3_clusters(sema_index *s, int c, int *out)
 {
     return c == 4 ? k3_max_clusters<KC, 4>(s, out) : c == 2 ? k3_max_clusters<KC, 2>(s, out) : k3_max_clusters<KC, 1>(s, out);
+}
+int k3_clusters_kc(sema_index *s, uint32_t kc, int c, int *out)
+{
+    return kc == 16 ? k3_clusters<16>(s, c, out) : kc == 32 ? k3_clusters<32>(s, c, out) : kc == 64 ? k3_clusters<64>(s, c, out)
+                    : k3_clusters<128>(s, c, out);
 }
 
 // Qd: nq x dim dense on the device.  Results: device arrays [nq*k], [nq*k], [nq].
@@ -340,16 +356,39 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     if (pair)
         rc = kc == 16 ? k3_pair_clusters<16>(s, &max_clusters) : kc == 32 ? k3_pair_clusters<32>(s, &max_clusters) : k3_pair_clusters<64>(s, &max_clusters);
     else
-        rc = kc == 16 ? k3_clusters<16>(s, csize, &max_clusters) : kc == 32 ? k3_clusters<32>(s, csize, &max_clusters) : kc == 64 ? k3_clusters<64>(s, csize, &max_clusters) : k3_clusters<128>(s, csize, &max_clusters);
+        rc = k3_clusters_kc(s, kc, csize, &max_clusters);
     if (rc) return rc;
     const uint32_t groups_all = q_ctas_pad / csize;             // clusters along the query axis
+
+    // Mixed cluster sizes.  Clusters of 4 are the most efficient shape per SM (one fetch from L2 serves four CTAs and no
+    // two clusters stream the same rows), but only 33 of them fit the GPCs of a B200 (132 SMs); clusters of 2 reach all
+    // 148 SMs.  So a stage is issued as TWO concurrent launches: clusters of 4 over as many row partitions as fit, and —
+    // on a second stream — clusters of 2 on the SMs the first launch leaves free (GPC remainders), each launch with its
+    // own slice of the rows (a 4-cluster partition gets 1.05x the rows of a 2-cluster one; measured flat between 1.01 and 1.09).
+    // 10M x 384 x 1024q, alternating A/B: single pass 5.67 -> 5.61 ms, three passes 15.12 -> 14.55 ms.
+    uint32_t mixA = 0, mixB = 0;
+    if (!pair && s->k3_mixed != 0 && s->k3_cluster == 0 && csize == 2 && q_ctas_pad % 4 == 0 && groups_all <= (uint32_t)max_clusters) {
+        int max4 = 0;
+        rc = k3_clusters_kc(s, kc, 4, &max4);
+        if (rc) return rc;
+        const uint32_t gA = q_ctas_pad / 4, gB = q_ctas_pad / 2;
+        mixA = (uint32_t)max4 / gA;
+        const uint32_t left = (uint32_t)s->num_sms > mixA * gA * 4 ? (uint32_t)s->num_sms - mixA * gA * 4 : 0;
+        mixB = (left / 2) / gB;
+        if (mixA == 0 || mixB == 0 || n_tiles < 16 * (mixA + mixB)) mixA = mixB = 0;
+    }
+    if (mixA && (!s->aux_stream)) {
+        CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
     // at most max_clusters cluster columns per launch; the clusters left over become row partitions
     for (uint32_t g0 = 0; g0 < groups_all; g0 += (uint32_t)max_clusters) {
         const uint32_t groups = (groups_all - g0) < (uint32_t)max_clusters ? (groups_all - g0) : (uint32_t)max_clusters;
         const uint32_t q_ctas = groups * csize;                 // CTAs along the query axis in this launch
         const uint32_t qt0 = g0 * csize * qt_per_cta;           // first query tile of this launch
         const uint32_t q_tiles = q_ctas * qt_per_cta;
-        uint32_t parts = (uint32_t)max_clusters / groups;
+        uint32_t parts = mixA ? mixA + mixB : (uint32_t)max_clusters / groups;
         if (parts > n_tiles) parts = n_tiles;
         if (parts < 1) parts = 1;
         const size_t nqp = (size_t)q_tiles * k3::TILE_Q;
@@ -365,15 +404,40 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         p.n_rows = n;
         p.n_tiles = n_tiles;
         p.parts = parts;
+        p.part_base = 0;
+        p.tile_first = 0;
+        p.tile_per = (n_tiles + parts - 1) / parts;
+        p.tile_end = n_tiles;
         p.dim = s->dim;
         p.fmt = (uint32_t)s->planes_fmt;
         p.prefetch = (uint32_t)s->k3_prefetch;
         p.debug = (uint32_t)s->k3_debug;
-        if (pair)
+        if (pair) {
+            const uint32_t n_super = (n_tiles + 1) / 2;
+            p.tile_per = 2 * ((n_super + parts - 1) / parts);   // whole super-tiles (two 64-row tiles) per partition
             rc = kc == 16 ? k3_launch_pair<16>(s, p, q_ctas) : kc == 32 ? k3_launch_pair<32>(s, p, q_ctas) : k3_launch_pair<64>(s, p, q_ctas);
-        else
-            rc = kc == 16 ? k3_launch_scan<16>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 32 ? k3_launch_scan<32>(s, p, q_ctas, csize, passes, qt_per_cta) : kc == 64 ? k3_launch_scan<64>(s, p, q_ctas, csize, passes, qt_per_cta)
-                          : k3_launch_scan<128>(s, p, q_ctas, csize, passes, qt_per_cta);
+        } else if (mixA) {
+            const double wA = s->k3_mix_w > 0 ? 1.0 + s->k3_mix_w / 100.0 : 1.05;   // rows of a 4-cluster partition per row of a 2-cluster partition
+            uint32_t perA = (uint32_t)((double)n_tiles * wA / (wA * mixA + mixB) + 0.999);
+            if ((uint64_t)perA * mixA > n_tiles) perA = n_tiles / mixA;
+            const uint32_t restB = n_tiles - perA * mixA;
+            k3::Params pa = p, pb = p;
+            pa.tile_per = perA;
+            pa.tile_end = perA * mixA;
+            pb.part_base = mixA;
+            pb.tile_first = perA * mixA;
+            pb.tile_per = (restB + mixB - 1) / mixB;
+            CK(cudaEventRecord(s->ev_fork, s->stream));          // the second launch also needs the padded queries
+            CK(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+            rc = k3_launch_scan_kc(s, kc, pa, q_ctas, 4, passes, qt_per_cta, mixA, s->stream);
+            if (rc) return rc;
+            rc = k3_launch_scan_kc(s, kc, pb, q_ctas, 2, passes, qt_per_cta, mixB, s->aux_stream);
+            if (rc) return rc;
+            CK(cudaEventRecord(s->ev_join, s->aux_stream));
+            CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));   // the re-scoring reads both launches' candidate lists
+        } else {
+            rc = k3_launch_scan_kc(s, kc, p, q_ctas, csize, passes, qt_per_cta, parts, s->stream);
+        }
         if (rc) return rc;
         const uint32_t q_first = qt0 * k3::TILE_Q;
         if (q_first >= nq) break;

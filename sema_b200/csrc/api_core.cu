@@ -271,6 +271,9 @@ int sema_index_destroy(sema_index *s)
     cudaFree(s->cand_thr); cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->ingest_stream) cudaStreamDestroy(s->ingest_stream);
+    if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     cudaGetLastError();
     delete s;
     return SEMA_OK;
@@ -661,6 +664,10 @@ int sema_index_set_scan_variant(sema_index *s, int variant)
 #ifdef SEMA_K3_PROBES
     if (variant >= 1000000) { s->k3_debug = variant - 1000000; return variant; }   // probe builds: wide probe masks
 #endif
+    if (variant >= 1300) return -1;
+    if (variant >= 1200) { s->k3_mix_w = variant - 1200; return variant; }    // 1200 + w: rows of a 4-cluster partition = (1 + w/100) x rows of a 2-cluster partition (0 = built-in)
+    if (variant >= 1102) return -1;
+    if (variant >= 1100) { s->k3_mixed = variant - 1100; return variant; }   // 1100 / 1101 = a K3 stage as one launch / as two concurrent launches (clusters of 4 + clusters of 2, default)
     if (variant >= 1000) return -1;
     if (variant >= 800) { s->k3_prefetch = variant - 800; return variant; }  // 800 + d = K3 producer prefetches into L2 d stages ahead (0 = off)
     if (variant >= 702) return -1;

@@ -135,6 +135,10 @@ struct sema_index {
     int k3_kc16 = 1;                    // single-pass stage with k <= 10 keeps 16 candidates per list (0 = 32) — tuning
     int k3_qt = 0;                      // 0 auto, 1 = one query tile per CTA even in the single-pass mode — tuning
     int k3_pair = 0;                    // single-pass stage: 0 = the single-CTA kernel (two query tiles per CTA, clusters of 2: 5.64 ms on config 3), 1 = CTA pairs (cta_group::2: 6.22 ms) — tuning
+    int k3_mixed = 1;                   // a K3 stage as two concurrent launches, clusters of 4 + clusters of 2 on the SMs left over (0 = one launch) — tuning
+    int k3_mix_w = 0;                   // mixed launch: row weight of a 4-cluster partition in percent above 1.00 (0 = built-in default) — tuning
+    cudaStream_t aux_stream = nullptr;  // second stream of the mixed launch, with its fork / join events
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int k3_prefetch = 0;                // L2 prefetch distance of K3's producer in pipeline stages (0 = none) — tuning
     int k3_prec = 0;                    // plane format preference: 0 = automatic (fp16 when every |x_i| <= 1024, else bf16), 1 = bf16 always
     int planes_fmt = 0;                 // format the planes are in now (k3::FMT_BF16 / FMT_FP16)

@@ -281,7 +281,10 @@ struct Params {
     float *cand_thr;              // [q_tiles*128][parts]      lowest approx score kept (-inf if list not full)
     uint32_t n_rows;              // visible rows
     uint32_t n_tiles;             // ceil(n_rows / 64)
-    uint32_t parts;               // row partitions (gridDim.y)
+    uint32_t parts;               // row partitions of the whole stage = candidate lists per query (all launches of a stage)
+    uint32_t part_base;           // this launch's first partition (a stage may be two concurrent launches with different
+                                  // cluster sizes that together fill every SM: see k3_stage)
+    uint32_t tile_first, tile_per, tile_end;   // this launch's partitions: tiles [tile_first + j*tile_per, ... + tile_per) clipped to tile_end
     uint32_t dim;
     uint32_t fmt;                 // FMT_BF16 / FMT_FP16: element format of the planes (and of the queries staged in TMEM)
     uint32_t prefetch;            // L2 prefetch distance of the producer, in pipeline stages (0 = none)
@@ -332,12 +335,11 @@ batch_scan_kernel(const Params p)
     // control flow and the MMA issue loop keeps descriptors / TMEM addresses in uniform registers (UIADD3 + UTCHMMA
     // instead of ~15 instructions with four R2UR per MMA, which made one issuing warp slower than the tensor pipe)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const uint32_t qt = blockIdx.x, part = blockIdx.y;   // this CTA's query tiles: qt*QT .. qt*QT + QT-1
+    const uint32_t qt = blockIdx.x, part = p.part_base + blockIdx.y;   // this CTA's query tiles: qt*QT .. qt*QT + QT-1
     const uint32_t kblocks = p.dim / BLOCK_K;            // stages per tile
     const uint32_t acols = p.dim / 2;                    // TMEM columns per query plane
     // contiguous tile range of this row partition
-    const uint32_t per = (p.n_tiles + p.parts - 1) / p.parts;
-    const uint32_t t0 = min(part * per, p.n_tiles), t1 = min(t0 + per, p.n_tiles);
+    const uint32_t t0 = min(p.tile_first + blockIdx.y * p.tile_per, p.tile_end), t1 = min(t0 + p.tile_per, p.tile_end);
 
     if (threadIdx.x == 0) {
         // a stage is released by one issuer per CTA of the cluster (QT = 1) or by both (QT = 2)

@@ -151,12 +151,12 @@ pair_scan_kernel(const Params p, const __grid_constant__ CUtensorMap tmap)
     const uint32_t crank = cluster_ctarank();
     const uint32_t half = crank & 1u;                    // 0 = leader of the pair
     const uint32_t leader_rank = crank & ~1u;
-    const uint32_t qt = blockIdx.x, part = blockIdx.y;
+    const uint32_t qt = blockIdx.x, part = p.part_base + blockIdx.y;
     const uint32_t acols = p.dim / 2;
     // row partition in units of super-tiles (2 consecutive 64-row tiles = one accumulator)
-    const uint32_t n_super = (p.n_tiles + 1) / 2;
-    const uint32_t per = (n_super + p.parts - 1) / p.parts;
-    const uint32_t u0 = min(part * per, n_super), u1 = min(u0 + per, n_super);
+    // (tile_first, tile_per and tile_end are even for this kernel: the host rounds them to super-tiles)
+    const uint32_t n_super = (p.tile_end + 1) / 2;
+    const uint32_t u0 = min(p.tile_first / 2 + blockIdx.y * (p.tile_per / 2), n_super), u1 = min(u0 + p.tile_per / 2, n_super);
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], 1); }

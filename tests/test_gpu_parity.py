@@ -504,7 +504,7 @@ def test_k3_query_scaling_and_format_choice(sema, oracle_c, qmag, xmag, want_fmt
 
 def test_k3_probe_settings_are_refused_by_the_shipped_library(sema):
     with sema.GpuIndex(384, 64) as idx:
-        for bad in (301, 302, 303, 316, 332, 364, 702, 800):
+        for bad in (301, 302, 303, 316, 332, 364, 702, 1000, 1102, 1300):
             assert idx.set_scan_variant(bad) == -1
         assert idx.set_scan_variant(308) == 308 and idx.set_scan_variant(300) == 300
 
