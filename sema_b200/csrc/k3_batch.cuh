@@ -60,6 +60,18 @@ constexpr int FMT_BF16 = 0;            // 8 significant bits, fp32's exponent ra
 constexpr int FMT_FP16 = 1;            // 11 significant bits: 8x tighter error bounds; needs |x_i| <= 1024 (queries are
                                        // scaled by a power of two in the kernel, rows are checked by the host)
 
+// How the kernels wait on their mbarriers (A/B switch; see ptx.cuh for the three forms)
+#if defined(SEMA_K3_WAIT_SPIN)
+#define K3_WAIT(bar, par) mbar_wait_spin(bar, par)
+#define K3_WAIT_EPI(bar, par) mbar_wait_spin(bar, par, 32)
+#elif defined(SEMA_K3_WAIT_NOHINT)
+#define K3_WAIT(bar, par) mbar_wait_cluster(bar, par)
+#define K3_WAIT_EPI(bar, par) mbar_wait_cluster(bar, par)
+#else
+#define K3_WAIT(bar, par) mbar_wait(bar, par)
+#define K3_WAIT_EPI(bar, par) mbar_wait(bar, par)
+#endif
+
 // Timing probes (Params::debug values that skip work and therefore give WRONG results) exist only in
 // builds made with -DSEMA_K3_PROBES (scripts/build_probe.sh); the shipped library ignores them.
 #ifdef SEMA_K3_PROBES
@@ -429,7 +441,7 @@ batch_scan_kernel(const Params p)
                         if (tp < t1)
                             bulk_prefetch_l2(p.planes + (size_t)tp * tile_bytes((int)p.dim) + (size_t)kp * STAGE_BYTES + crank * SLICE, SLICE);
                     }
-                    mbar_wait(&empty[stage], phase ^ 1);     // all C consumers released this stage
+                    K3_WAIT(&empty[stage], phase ^ 1);       // all C consumers released this stage
                     mbar_expect_tx(&full[stage], STAGE);
                     // the planes hold [hi | lo] per k-block; a 1-pass stage fetches the hi half only
                     if (C == 1)
@@ -463,10 +475,10 @@ batch_scan_kernel(const Params p)
                 const uint32_t buf = dual ? w : (it & 1);
                 const uint32_t use = dual ? it : (it >> 1);
                 const uint32_t d_tmem = tmem + acc_col + buf * TILE_N;
-                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                K3_WAIT(&acc_empty[buf], (use & 1) ^ 1);
                 tc_fence_after();
                 for (uint32_t kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[st], ph);
+                    K3_WAIT(&full[st], ph);
                     tc_fence_after();
                     const uint32_t sb = smem_u32(ring + st * STAGE);
 #pragma unroll
@@ -511,7 +523,7 @@ batch_scan_kernel(const Params p)
                 int cnt = qi ? cnt1 : cnt0, min_pos = qi ? mp1 : mp0;
                 float *lsc = list_sc + qi * KC * TILE_Q;
                 uint32_t *lrow = list_row + qi * KC * TILE_Q;
-                mbar_wait(&acc_full[buf], use & 1);
+                K3_WAIT_EPI(&acc_full[buf], use & 1);
                 tc_fence_after();
                 uint32_t r[2][32];
                 tmem_ld32(lane_addr + buf * TILE_N, r[0]);
