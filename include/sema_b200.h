@@ -314,7 +314,7 @@ int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float 
  * stage on the single-CTA kernel (default) / on CTA pairs (tcgen05 cta_group::2); 800 + d = K3 producer
  * prefetches into L2 d stages ahead (default 0: measured no gain); 1100 / 1101 = a K3 stage as one launch / as
  * two concurrent launches, clusters of 4 plus clusters of 2 on the SMs those leave free (default); 1200 + w = row
- * weight of a 4-cluster partition in that split, percent above 1 (0 = built-in 1.05); negative = query.
+ * weight of a 4-cluster partition in that split, 0.70 + w / 100 (0 = built-in 1.05); negative = query.
  * Returns the value set, or -1 for a value this build does not have. */
 int sema_index_set_scan_variant(sema_index *idx, int variant);
 /* number of kernels this handle has launched so far */

@@ -38,8 +38,8 @@ def timed(mode, settings, reps=3):
     for _ in range(reps): idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
     e1.record(stream); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-cases = [("1pass one launch", 3, [700, 100, 1100])] + [(f"1pass mixed w=1.{w:02d}", 3, [700, 100, 1101, 1200 + w]) for w in (1, 5, 9, 14, 20)] + \
-        [("3pass one launch", 2, [700, 100, 1100])] + [(f"3pass mixed w=1.{w:02d}", 2, [700, 100, 1101, 1200 + w]) for w in (1, 5, 9, 14, 20)]
+cases = [(f"1pass mixed w={0.70 + w / 100:.2f}", 3, [700, 100, 1101, 1200 + w]) for w in (5, 15, 22, 30, 35)] + \
+        [(f"3pass mixed w={0.70 + w / 100:.2f}", 2, [700, 100, 1101, 1200 + w]) for w in (5, 15, 22, 30, 35)]
 res = {n: [] for n, _, _ in cases}
 for rnd in range(4):
     for n, mode, st in (cases if rnd % 2 == 0 else cases[::-1]):

@@ -396,10 +396,13 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         if (rc) return rc;
         rc = ensure(reinterpret_cast<void **>(&s->cand_thr), &s->thr_cap, nqp * parts * sizeof(float));
         if (rc) return rc;
+        rc = ensure(reinterpret_cast<void **>(&s->cand_sc), &s->cand_sc_cap, nqp * parts * kc * sizeof(float));
+        if (rc) return rc;
         k3::Params p;
         p.planes = s->planes;
         p.Q = s->Qpad_dev + (size_t)qt0 * k3::TILE_Q * s->dim;
         p.cand_rows = s->cand_rows;
+        p.cand_sc = s->cand_sc;
         p.cand_thr = s->cand_thr;
         p.n_rows = n;
         p.n_tiles = n_tiles;
@@ -417,7 +420,7 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
             p.tile_per = 2 * ((n_super + parts - 1) / parts);   // whole super-tiles (two 64-row tiles) per partition
             rc = kc == 16 ? k3_launch_pair<16>(s, p, q_ctas) : kc == 32 ? k3_launch_pair<32>(s, p, q_ctas) : k3_launch_pair<64>(s, p, q_ctas);
         } else if (mixA) {
-            const double wA = s->k3_mix_w > 0 ? 1.0 + s->k3_mix_w / 100.0 : 1.05;   // rows of a 4-cluster partition per row of a 2-cluster partition
+            const double wA = s->k3_mix_w > 0 ? 0.70 + s->k3_mix_w / 100.0 : 1.05;   // rows of a 4-cluster partition per row of a 2-cluster partition
             uint32_t perA = (uint32_t)((double)n_tiles * wA / (wA * mixA + mixB) + 0.999);
             if ((uint64_t)perA * mixA > n_tiles) perA = n_tiles / mixA;
             const uint32_t restB = n_tiles - perA * mixA;
@@ -446,6 +449,7 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
         r.X = reinterpret_cast<const float4 *>(s->X);
         r.Q = p.Q;
         r.cand_rows = s->cand_rows;
+        r.cand_sc = s->cand_sc;
         r.cand_thr = s->cand_thr;
         r.res_ids = ids_d + (size_t)q_first * k;
         r.res_scores = sc_d + (size_t)q_first * k;

@@ -268,7 +268,7 @@ int sema_index_destroy(sema_index *s)
     cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
     cudaFree(s->qscratch); cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
     cudaFree(s->q_aligned); cudaFree(s->sub_q); cudaFree(s->sub_ids); cudaFree(s->sub_sc); cudaFree(s->sub_nf); cudaFree(s->sub_idx);
-    cudaFree(s->cand_thr); cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
+    cudaFree(s->cand_thr); cudaFree(s->cand_sc); cudaFree(s->flags_dev); cudaFreeHost(s->flags_pin);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->ingest_stream) cudaStreamDestroy(s->ingest_stream);
     if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
@@ -665,7 +665,7 @@ int sema_index_set_scan_variant(sema_index *s, int variant)
     if (variant >= 1000000) { s->k3_debug = variant - 1000000; return variant; }   // probe builds: wide probe masks
 #endif
     if (variant >= 1300) return -1;
-    if (variant >= 1200) { s->k3_mix_w = variant - 1200; return variant; }    // 1200 + w: rows of a 4-cluster partition = (1 + w/100) x rows of a 2-cluster partition (0 = built-in)
+    if (variant >= 1200) { s->k3_mix_w = variant - 1200; return variant; }    // 1200 + w: rows of a 4-cluster partition = (0.70 + w/100) x rows of a 2-cluster partition (0 = built-in 1.05)
     if (variant >= 1102) return -1;
     if (variant >= 1100) { s->k3_mixed = variant - 1100; return variant; }   // 1100 / 1101 = a K3 stage as one launch / as two concurrent launches (clusters of 4 + clusters of 2, default)
     if (variant >= 1000) return -1;

@@ -127,6 +127,8 @@ struct sema_index {
     float *Qpad_dev = nullptr;
     uint32_t *cand_rows = nullptr;
     float *cand_thr = nullptr;
+    float *cand_sc = nullptr;
+    size_t cand_sc_cap = 0;
     uint32_t *flags_dev = nullptr, *flags_pin = nullptr;
     size_t qpad_cap = 0, cand_cap = 0, thr_cap = 0, flags_cap = 0;
     int batch_mode = 0;                 // 0 auto, 1 always the K2 loop, 2 K3 bf16x3 whenever the shape allows, 3 K3 single bf16 pass

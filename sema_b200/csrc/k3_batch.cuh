@@ -290,6 +290,7 @@ struct Params {
     const unsigned char *planes;  // pre-tiled hi/lo planes
     const float *Q;               // q_tiles*128 x dim fp32 (zero padded rows)
     uint32_t *cand_rows;          // [q_tiles*128][parts][KC]  local row ids (0xFFFFFFFF = empty)
+    float *cand_sc;               // [q_tiles*128][parts][KC]  their tensor-core scores, in the query's own scale (-inf = empty)
     float *cand_thr;              // [q_tiles*128][parts]      lowest approx score kept (-inf if list not full)
     uint32_t n_rows;              // visible rows
     uint32_t n_tiles;             // ceil(n_rows / 64)
@@ -605,8 +606,14 @@ batch_scan_kernel(const Params p)
             const uint32_t *lrow = list_row + qi * KC * TILE_Q;
             const size_t q = ((size_t)qt * QT + qi) * TILE_Q + m;
             uint32_t *out = p.cand_rows + (q * p.parts + part) * KC;
-            for (int i = 0; i < KC; ++i) out[i] = i < cnt ? lrow[i * TILE_Q + m] : 0xffffffffu;
-            p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr / (qi ? qscale1 : qscale0) : -INFINITY;   // back to q's own scale (exact)
+            float *out_sc = p.cand_sc + (q * p.parts + part) * KC;
+            const float *lsc = list_sc + qi * KC * TILE_Q;
+            const float unscale = 1.0f / (qi ? qscale1 : qscale0);          // a power of two: exact
+            for (int i = 0; i < KC; ++i) {
+                out[i] = i < cnt ? lrow[i * TILE_Q + m] : 0xffffffffu;
+                out_sc[i] = i < cnt ? lsc[i * TILE_Q + m] * unscale : -INFINITY;
+            }
+            p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr * unscale : -INFINITY;   // back to q's own scale (exact)
         }
     }
 
@@ -624,6 +631,7 @@ struct RescoreParams {
     const float4 *X;           // fp32 matrix, row stride ld4
     const float *Q;            // padded queries, row stride dim
     const uint32_t *cand_rows; // [q][parts*KC]
+    const float *cand_sc;      // [q][parts*KC] tensor-core scores of the candidates
     const float *cand_thr;     // [q][parts]
     uint64_t *res_ids;         // [nq][k]
     float *res_scores;         // [nq][k]
@@ -654,11 +662,65 @@ rescore_kernel(const RescoreParams p)
     const uint32_t nv = p.dim / 4;  // float4 per row (dim % 64 == 0)
     const float4 *qp = reinterpret_cast<const float4 *>(p.Q + (size_t)q * p.dim);
     const uint32_t total = p.parts * p.kc;
+    __shared__ float sm_cut;
+    // |q|, computed on the query scaled into [0.5, 1) by a power of two so that |q|^2 can neither overflow nor
+    // vanish (the L2 proof below needs the plain |q|^2, which is as representable as the distances themselves)
+    float amax = 0.0f;
+    for (uint32_t v = lane; v < nv; v += 32) {
+        const float4 f = qp[v];
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y))), fmaxf(fabsf(f.z), fabsf(f.w)));
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, d));
+    const float qs = query_scale(amax);
+    float qq = 0.0f, qqs = 0.0f;
+    for (uint32_t v = lane; v < nv; v += 32) {
+        const float4 f = qp[v];
+        qq = accum4<METRIC_COSINE>(qq, f, f);
+        const float4 g = make_float4(f.x * qs, f.y * qs, f.z * qs, f.w * qs);
+        qqs = accum4<METRIC_COSINE>(qqs, g, g);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { qq += __shfl_xor_sync(FULL, qq, d); qqs += __shfl_xor_sync(FULL, qqs, d); }
+    const float qnorm = sqrtf(qqs) / qs;
+    const float err_bound = qnorm * (p.err_rel * sqrtf(p.max_norm2[0]) + p.err_abs);
+
+    // Which candidates are worth an exact re-scoring?  Let T be the k-th best TENSOR-CORE score among all candidates:
+    // k candidates have exact score >= T - err, so a candidate whose tensor-core score is below T - 2 err has an exact
+    // score below the exact k-th best and cannot be in the result (L2 metric over rows whose |x|^2 differ by at most
+    // mx - mn: below T - 2 err - (mx - mn) / 2).  That leaves ~k of the parts * KC candidates (592 for config 3).
     WarpTopK<M> top;
+    top.init();
+    for (uint32_t i0 = warp * 32; i0 < total; i0 += SCAN_WARPS * 32) {
+        const uint32_t i = i0 + lane;
+        const float a = i < total ? p.cand_sc[(size_t)q * total + i] : -INFINITY;
+        top.offer(make_key(a, i), a > -INFINITY, lane, k);
+    }
+    block_merge<M, SCAN_WARPS>(top, sm_keys, warp, lane, k);
+    if (warp == 0) {
+        const int kj0 = (k - 1) >> 5, kl0 = (k - 1) & 31;
+        uint64_t kt = 0;
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            if (j == kj0) kt = top.v[j];
+        kt = __shfl_sync(FULL, kt, kl0);
+        if (lane == 0) {
+            float cut = -INFINITY;
+            if (kt != 0) {
+                const float t = key_rank(kt);
+                cut = t - 2.0f * err_bound - 1e-6f * fabsf(t) - 1e-30f;
+                if (METRIC == METRIC_L2) cut -= 0.5f * (p.max_norm2[0] - p.max_norm2[1]) * 1.000001f;
+            }
+            sm_cut = cut;
+        }
+    }
+    __syncthreads();
+    const float cut = sm_cut;
     top.init();
     for (uint32_t i = warp; i < total; i += SCAN_WARPS) {
         const uint32_t row = p.cand_rows[(size_t)q * total + i];
         if (row == 0xffffffffu) continue;  // warp-uniform
+        if (!(p.cand_sc[(size_t)q * total + i] >= cut)) continue;   // warp-uniform: cannot reach the exact top-k
         const float4 *xp = p.X + (size_t)row * p.ld4;
         float acc = 0.0f;
         for (uint32_t v = lane; v < nv; v += 32) acc = accum4<METRIC>(acc, xp[v], qp[v]);
@@ -683,28 +745,7 @@ rescore_kernel(const RescoreParams p)
         for (int j = 0; j < M; ++j)
             if (j == kj) kk = top.v[j];
         kk = __shfl_sync(FULL, kk, kl);
-        // |q|, computed on the query scaled into [0.5, 1) by a power of two so that |q|^2 can neither overflow nor
-        // vanish (the L2 proof below needs the plain |q|^2, which is as representable as the distances themselves)
-        float amax = 0.0f;
-        for (uint32_t v = lane; v < nv; v += 32) {
-            const float4 f = qp[v];
-            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y))), fmaxf(fabsf(f.z), fabsf(f.w)));
-        }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, d));
-        const float qs = query_scale(amax);
-        float qq = 0.0f, qqs = 0.0f;
-        for (uint32_t v = lane; v < nv; v += 32) {
-            const float4 f = qp[v];
-            qq = accum4<METRIC_COSINE>(qq, f, f);
-            const float4 g = make_float4(f.x * qs, f.y * qs, f.z * qs, f.w * qs);
-            qqs = accum4<METRIC_COSINE>(qqs, g, g);
-        }
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) { qq += __shfl_xor_sync(FULL, qq, d); qqs += __shfl_xor_sync(FULL, qqs, d); }
         if (lane == 0) {
-            const float qnorm = sqrtf(qqs) / qs;
-            const float err_bound = qnorm * (p.err_rel * sqrtf(p.max_norm2[0]) + p.err_abs);
             bool proven = true;
             if (worst > -INFINITY) {
                 if (METRIC == METRIC_L2)   // key_rank = -distance; slack for the fp32 evaluation of the bound itself

@@ -369,8 +369,13 @@ pair_scan_kernel(const Params p, const __grid_constant__ CUtensorMap tmap)
         // publish this partition's candidates for the CTA's queries
         const size_t q = (size_t)qt * TILE_Q + m;
         uint32_t *out = p.cand_rows + (q * p.parts + part) * KC;
-        for (int i = 0; i < KC; ++i) out[i] = i < cnt ? list_row[i * TILE_Q + m] : 0xffffffffu;
-        p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr / qscale : -INFINITY;
+        float *out_sc = p.cand_sc + (q * p.parts + part) * KC;
+        const float unscale = 1.0f / qscale;                                // a power of two: exact
+        for (int i = 0; i < KC; ++i) {
+            out[i] = i < cnt ? list_row[i * TILE_Q + m] : 0xffffffffu;
+            out_sc[i] = i < cnt ? list_sc[i * TILE_Q + m] * unscale : -INFINITY;
+        }
+        p.cand_thr[q * p.parts + part] = (cnt == KC) ? thr * unscale : -INFINITY;
     }
 
     tc_fence_before();
