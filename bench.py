@@ -1189,7 +1189,7 @@ def run_batch_sharded(a):
         line = {
             "metric": f"qps_batched_{nq}q_exact_top{k}_cosine_{a.rows}x{a.dim}_fp32", "value": nq / (dev_ms * 1e-3),
             "unit": "queries/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": dev_ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": BATCH_MODES.get(a.batch_mode, BATCH_MODES[2])[1], "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": batch_modes(idx.batch_precision_active).get(a.batch_mode, batch_modes(idx.batch_precision_active)[2])[1], "data": "synthetic",
             "config": {"workload": f"{a.rows}x{a.dim} fp32 corpus row-sharded over {world} GPUs, batches of {nq} queries, exact top-{k}",
                        "batch_mode": a.batch_mode, "rows_per_gpu": hi - lo, "exchange": "nccl all-gather of nq x k packed keys + batched K4",
                        "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks"},
