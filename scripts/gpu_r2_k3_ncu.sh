@@ -2,11 +2,11 @@
 # 2M-row corpus; each capture only after the same command exited 0 without ncu
 mkdir -p gpurun_out
 TAG=${TAG:-r02c}
-for V in "3 0 batch_scan single" "2 0 batch_scan x3" "3 1 pair_scan pair"; do
+for V in "3 0 batch_scan single" "2 0 batch_scan x3"; do
 set -- $V
 CMD="python bench.py --workload batch --rows 2000000 --steps 1 --batch-mode $1 --k3-pair $2"
 $CMD > gpurun_out/plain_k3_$4.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:$3 -s 2 -c 1 -o gpurun_out/k3_$4_$TAG -f $CMD > gpurun_out/ncu_k3_$4.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:$3 -s 4 -c 2 -o gpurun_out/k3_$4_$TAG -f $CMD > gpurun_out/ncu_k3_$4.log 2>&1
 tail -c 200 gpurun_out/plain_k3_$4.log; tail -2 gpurun_out/ncu_k3_$4.log
 done
 # launch list of the batch workload (kernel shares of a step)
