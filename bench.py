@@ -798,7 +798,10 @@ def run_ours(a):
             stream_ids = ids_s[:a.steps].cpu().numpy().astype(np.uint64)
             stream_sc = sc_s[:a.steps].cpu().numpy()
 
-        # ---- end-to-end region: host query in, host results out, through the public call
+        # ---- end-to-end region: host query in, host results out, through the public call.  The clock sampler keeps
+        # running but ten times less often: NVML queries take driver locks, and a host-driven loop of 2 ms calls is
+        # exposed to that where a pre-enqueued device stream is not (the spread of this region is reported in `repeats`)
+        clk.period = 0.2
         e2e_all, e2e_lat, e2e_pipe_ms = [], None, None
         if a.staged_host_path:
             idx.set_scan_variant(500)

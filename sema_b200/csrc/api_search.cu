@@ -259,9 +259,14 @@ int host_query_wait(sema_index *s, uint64_t ticket, uint32_t k, uint64_t *row_id
     // that a failed launch / faulting kernel surfaces as an error instead of an endless wait.
     const unsigned char *slot = s->res_map + (ticket % RES_SLOTS) * RES_SLOT_BYTES;
     volatile const uint64_t *flag = reinterpret_cast<volatile const uint64_t *>(slot + RES_MAP_FLAG_OFF);
+    static const uint32_t query_mask = [] {       // SEMA_POLL_QUERY_SHIFT: stream query every 2^shift polls (measurement knob)
+        const char *e = getenv("SEMA_POLL_QUERY_SHIFT");
+        const int sh = e ? atoi(e) : 14;
+        return (uint32_t)((1u << (sh < 4 ? 4 : (sh > 30 ? 30 : sh))) - 1u);
+    }();
     for (uint32_t spin = 1;; ++spin) {
         if (*flag == ticket) break;
-        if ((spin & 0x3fffu) == 0) {
+        if ((spin & query_mask) == 0) {
             const cudaError_t e = cudaStreamQuery(s->stream);
             if (e == cudaSuccess) {
                 if (*flag == ticket) break;
