@@ -605,6 +605,71 @@ def test_k3_prefetch_knob_does_not_change_results(sema, oracle_c):
         O.check_parity(out[0][0][i], out[0][1][i], r[0][i], r[1][i])
 
 
+def test_k3_format_follows_later_appends(sema, oracle_c):
+    """fp16 halves while every element is <= 1024; an append that brings larger elements re-splits every plane as
+    bf16 on the next batch (and results stay exact on both sides of the switch)."""
+    n, d, k, nq = 20000, 384, 10, 160
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    big = (_unit(3, 2000, d) * np.float32(5000.0)).astype(np.float32)
+    with sema.GpuIndex(d, n + 2000) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, k)
+        assert idx.batch_precision_active == 1
+        r = oracle_c.scan_batch(X, Q, k)
+        for i in range(0, nq, 9):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+        idx.append(big, normalize=False)
+        X2 = np.concatenate([X, big])
+        for mode in (0, 2, 3):
+            idx.set_batch_mode(mode)
+            ids, sc, nf = idx.search_batch(Q, k)
+            assert idx.batch_precision_active == 0
+            idx.set_batch_mode(1)
+            ids2, sc2, nf2 = idx.search_batch(Q, k)
+            assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
+        r = oracle_c.scan_batch(X2, Q[:8], k)
+        for i in range(8):
+            O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+
+
+def test_k3_repeated_batches_are_stable(sema, oracle_c):
+    """A stage is two concurrent launches on two streams joined by events, its candidate buffers are reused by the
+    next batch, and the cascade re-enters the stage for sub-batches: 60 batches back to back, modes alternating, device
+    buffers, every result identical to the first of its mode (any race between the streams or between consecutive
+    batches shows up as a difference)."""
+    import torch
+    n, d, k, nq = 200_000, 384, 10, 300
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    dev = torch.device("cuda:0")
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        Qd = torch.from_numpy(Q).to(dev)
+        ids_d = torch.zeros(nq * k, dtype=torch.int64, device=dev)
+        sc_d = torch.zeros(nq * k, dtype=torch.float32, device=dev)
+        nf_d = torch.zeros(nq, dtype=torch.int32, device=dev)
+        idx.set_stream(torch.cuda.current_stream().cuda_stream)
+        first = {}
+        for it in range(60):
+            mode = (0, 3, 2)[it % 3]
+            idx.set_batch_mode(mode)
+            ids_d.zero_(); sc_d.zero_()
+            idx.search_batch_device(Qd.data_ptr(), nq, k, ids_d.data_ptr(), sc_d.data_ptr(), nf_d.data_ptr())
+            torch.cuda.synchronize()
+            got = (ids_d.cpu().numpy().copy(), sc_d.cpu().numpy().copy())
+            if mode not in first:
+                first[mode] = got
+            else:
+                assert np.array_equal(got[0], first[mode][0]) and np.array_equal(got[1], first[mode][1]), f"batch {it} (mode {mode}) differs"
+        idx.set_stream(None)
+    assert np.array_equal(first[0][0], first[2][0]) and np.array_equal(first[0][0], first[3][0])
+    r = oracle_c.scan_batch(X, Q[:8], k)
+    ids = first[0][0].astype(np.uint64).reshape(nq, k); sc = first[0][1].reshape(nq, k)
+    for i in range(8):
+        O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+
+
 def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
     # dim 1024 is served by K2 (one pass per query); the L2 metric over unit rows by K3: same results
     X = _unit(1, 5000, 1024)
