@@ -318,7 +318,14 @@ int k3_stage(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k
     SEMA_NVTX("sema.K3.stage(scan+rescore)");
     // candidates kept per (query, row partition): the list minimum is the admission threshold and every
     // insertion re-scans the list, so the list is only as long as the exactness proof needs
-    const uint32_t kc = (k <= 10 && passes == 1 && s->k3_kc16 != 0) ? 16 : (k <= 16 ? 32 : (k <= 48 ? 64 : 128));
+    // Single-pass stage: SHORT lists.  Insertions per list grow like KC ln(rows / KC) and each one re-scans the list, so
+    // the epilogue's work grows like KC^2: with KC = 128 a k = 50 batch took 17.8 ms against 5.4 ms at k = 10.  A
+    // partition only needs its list to reach below the global k-th score, and with ~37 partitions it holds k / 37 of the
+    // top k on average, so 16 (k <= 10), 32 (k <= 50) or 64 entries prove every query unless the neighbours cluster in
+    // one partition (rows of one document are adjacent) — those queries fail the proof and the cascade re-runs them in
+    // the three-pass stage, whose lists are long (32 / 64 / 128).
+    const uint32_t kc = passes == 1 ? ((k <= 10 && s->k3_kc16 != 0) ? 16 : (k <= 50 ? 32 : 64))
+                                    : (k <= 16 ? 32 : (k <= 48 ? 64 : 128));
     const uint32_t n_tiles = (n + k3::TILE_N - 1) / k3::TILE_N;
     const uint32_t q_tiles_all = (nq + k3::TILE_Q - 1) / k3::TILE_Q;
     int rc;

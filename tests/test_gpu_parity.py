@@ -670,6 +670,40 @@ def test_k3_repeated_batches_are_stable(sema, oracle_c):
         O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
 
 
+def test_k3_k50_with_all_neighbours_in_one_partition(sema, oracle_c):
+    """k = 50 (the reference's SEARCH_RESULTS_LIMIT) with the single-pass stage's short lists (32 entries per row
+    partition): when all 50 neighbours of a query sit next to each other (the chunks of one document) one partition's
+    list overflows, the proof fails for that query and the cascade's next stage (long lists) or K2 answers it — exactly."""
+    n, d, k, nq = 60000, 384, 50, 140
+    rng = np.random.default_rng(11)
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    for qi in (0, 1, 2, 3, 4, 5):
+        u = Q[qi].astype(np.float64)
+        for i in range(80):                                       # 80 planted rows, contiguous, cosines 0.95 .. 0.79
+            v = rng.standard_normal(d)
+            v -= v.dot(u) * u
+            v /= np.linalg.norm(v)
+            a = 0.95 - i * 2e-3
+            X[7000 * qi + 100 + i] = (a * u + np.sqrt(1 - a * a) * v).astype(np.float32)
+    X = O.normalize(X)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        ids, sc, nf = idx.search_batch(Q, k)                      # automatic mode: cascade
+        served, fallbacks = idx.batch_stats()
+        cascaded = idx.batch_cascaded
+        idx.set_batch_mode(1)
+        ids2, sc2, nf2 = idx.search_batch(Q, k)
+    assert served == nq and (nf == k).all()
+    assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
+    assert cascaded + fallbacks >= 6                              # the six clustered queries needed more than the short lists
+    for qi in range(6):
+        assert ids[qi, :50].tolist() == [7000 * qi + 100 + i for i in range(50)]
+    r = oracle_c.scan_batch(X, Q[:10], k)
+    for i in range(10):
+        O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
+
+
 def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
     # dim 1024 is served by K2 (one pass per query); the L2 metric over unit rows by K3: same results
     X = _unit(1, 5000, 1024)
