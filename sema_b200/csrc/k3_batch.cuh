@@ -221,6 +221,65 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
     return d;
 }
 
+// ---------------------------------------------------------------- candidate lists
+// A thread's candidate list lives in shared memory as column m of [KC][128] arrays.  Lists of 16 entries are kept
+// unordered and re-scanned for their minimum after every insertion (16 loads); longer lists are binary MIN-HEAPS once
+// they are full, so replacing the minimum costs 2 log2(KC) loads instead of KC.
+template <int KC>
+__device__ __forceinline__ void heap_sift_down(float *lsc, uint32_t *lrow, int m, int i, float v, uint32_t r)
+{
+    while (true) {
+        int c = 2 * i + 1;
+        if (c >= KC) break;
+        float a = lsc[c * TILE_Q + m];
+        if (c + 1 < KC) {
+            const float b = lsc[(c + 1) * TILE_Q + m];
+            if (b < a) { a = b; ++c; }
+        }
+        if (!(a < v)) break;
+        lsc[i * TILE_Q + m] = a;
+        lrow[i * TILE_Q + m] = lrow[c * TILE_Q + m];
+        i = c;
+    }
+    lsc[i * TILE_Q + m] = v;
+    lrow[i * TILE_Q + m] = r;
+}
+// One survivor (score v above the admission threshold, corpus row r) enters the list; returns the new threshold
+// (-inf until the list is full).  cnt / min_pos are the thread's list state (min_pos only used by the KC = 16 form).
+template <int KC>
+__device__ __forceinline__ float list_insert(float *lsc, uint32_t *lrow, int m, float v, uint32_t r, int &cnt, int &min_pos, float thr)
+{
+    if constexpr (KC <= 16) {
+        const int slot = cnt < KC ? cnt : min_pos;
+        lsc[slot * TILE_Q + m] = v;
+        lrow[slot * TILE_Q + m] = r;
+        if (cnt < KC) ++cnt;
+        if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
+            float mn = lsc[m];
+            int mp = 0;
+#pragma unroll 8
+            for (int i = 1; i < KC; ++i) {
+                const float sv = lsc[i * TILE_Q + m];
+                if (sv < mn) { mn = sv; mp = i; }
+            }
+            min_pos = mp;
+            return mn;
+        }
+        return thr;
+    } else {
+        if (cnt < KC) {
+            lsc[cnt * TILE_Q + m] = v;
+            lrow[cnt * TILE_Q + m] = r;
+            if (++cnt < KC) return thr;
+            for (int i = KC / 2 - 1; i >= 0; --i)          // the list has just filled up: heapify once
+                heap_sift_down<KC>(lsc, lrow, m, i, lsc[i * TILE_Q + m], lrow[i * TILE_Q + m]);
+        } else {
+            heap_sift_down<KC>(lsc, lrow, m, 0, v, r);      // v replaces the minimum at the root
+        }
+        return lsc[m];
+    }
+}
+
 // ---------------------------------------------------------------- plane builder
 // X (fp32, row stride ld) rows [row_begin, row_end) -> pre-tiled bf16 hi/lo planes.
 // One thread per (row, 8-element k-chunk); consecutive threads write consecutive 16 B.
@@ -576,22 +635,7 @@ batch_scan_kernel(const Params p)
                         for (int e = 0; e < 32; ++e) bits = (e == c) ? r[h][e] : bits;   // register select
                         const float v = __uint_as_float(bits);
                         if (!(v > thr)) continue;                 // the threshold may have risen meanwhile
-                        const int slot = cnt < KC ? cnt : min_pos;
-                        lsc[slot * TILE_Q + m] = v;
-                        lrow[slot * TILE_Q + m] = row0 + h * 32 + c;
-                        if (cnt < KC) ++cnt;
-                        if (PROBES && p.debug == 3 && cnt == KC) { thr = fmaxf(thr, v * 0.5f); continue; }   // probe: no rescan
-                        if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
-                            float mn = lsc[m];
-                            int mp = 0;
-#pragma unroll 8
-                            for (int i = 1; i < KC; ++i) {
-                                const float sv = lsc[i * TILE_Q + m];
-                                if (sv < mn) { mn = sv; mp = i; }
-                            }
-                            thr = mn;
-                            min_pos = mp;
-                        }
+                        thr = list_insert<KC>(lsc, lrow, m, v, row0 + h * 32 + c, cnt, min_pos, thr);
                     }
                 }
                 if (qi) { thr1 = thr; cnt1 = cnt; mp1 = min_pos; }

@@ -348,21 +348,7 @@ pair_scan_kernel(const Params p, const __grid_constant__ CUtensorMap tmap)
                     for (int e = 0; e < 32; ++e) bits = (e == c) ? r[h][e] : bits;   // register select
                     const float v = __uint_as_float(bits);
                     if (!(v > thr)) continue;                 // the threshold may have risen meanwhile
-                    const int slot = cnt < KC ? cnt : min_pos;
-                    list_sc[slot * TILE_Q + m] = v;
-                    list_row[slot * TILE_Q + m] = row0 + h * 32 + c;
-                    if (cnt < KC) ++cnt;
-                    if (cnt == KC) {  // (re)locate the minimum: it is the admission threshold
-                        float mn = list_sc[m];
-                        int mp = 0;
-#pragma unroll 8
-                        for (int i = 1; i < KC; ++i) {
-                            const float sv = list_sc[i * TILE_Q + m];
-                            if (sv < mn) { mn = sv; mp = i; }
-                        }
-                        thr = mn;
-                        min_pos = mp;
-                    }
+                    thr = list_insert<KC>(list_sc, list_row, m, v, row0 + h * 32 + c, cnt, min_pos, thr);
                 }
             }
         }
