@@ -249,7 +249,12 @@ __device__ __forceinline__ void heap_sift_down(float *lsc, uint32_t *lrow, int m
 template <int KC>
 __device__ __forceinline__ float list_insert(float *lsc, uint32_t *lrow, int m, float v, uint32_t r, int &cnt, int &min_pos, float thr)
 {
-    if constexpr (KC <= 16) {
+#ifdef SEMA_K3_HEAP16
+    constexpr int LINEAR_MAX = 8;
+#else
+    constexpr int LINEAR_MAX = 16;
+#endif
+    if constexpr (KC <= LINEAR_MAX) {
         const int slot = cnt < KC ? cnt : min_pos;
         lsc[slot * TILE_Q + m] = v;
         lrow[slot * TILE_Q + m] = r;
