@@ -704,6 +704,29 @@ def test_k3_k50_with_all_neighbours_in_one_partition(sema, oracle_c):
         O.check_parity(ids[i], sc[i], r[0][i], r[1][i])
 
 
+@pytest.mark.parametrize("nq", [20000, 40000])
+def test_k3_very_large_batches(sema, oracle_c, nq):
+    """More query tiles than resident clusters: the stage splits the query axis over several launches (40 000 queries
+    = 157 CTAs of two tiles > 74 clusters of 2); every query still equals the single-query kernel and the oracle."""
+    n, d, k = 6000, 384, 10
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, normalize=False)
+        for mode in (0, 2):
+            idx.set_batch_mode(mode)
+            q0, _ = idx.batch_stats()
+            ids, sc, nf = idx.search_batch(Q, k)
+            assert idx.batch_stats()[0] - q0 == nq and (nf == k).all()
+            sel = np.arange(0, nq, 397)
+            for i in sel[:40]:
+                r_ids, r_sc = idx.search(Q[i], k)
+                assert np.array_equal(ids[i], r_ids) and np.array_equal(sc[i], r_sc)
+    r = oracle_c.scan_batch(X, Q[nq - 8:], k)
+    for j in range(8):
+        O.check_parity(ids[nq - 8 + j], sc[nq - 8 + j], r[0][j], r[1][j])
+
+
 def test_k3_auto_mode_and_unsupported_shapes_use_k2(sema, oracle_c):
     # dim 1024 is served by K2 (one pass per query); the L2 metric over unit rows by K3: same results
     X = _unit(1, 5000, 1024)
