@@ -64,6 +64,15 @@ typedef int (*sema_embed_fn)(void *user, const char *text, float *out, uint32_t 
  * the address space only, 0 = no bound short of the 32-bit row ids — the reference's table has no
  * declared size either. */
 int sema_store_create(int device, uint32_t dim, uint64_t capacity_rows, int normalize, sema_store **out);
+/* The same store over several GPUs of the box — still ONE handle in ONE process, which is what the reference is
+ * (one StorageManager owned by the Engine, src/storage/mod.rs:13-16, src/tui/engine.rs:30).  The table is dealt out
+ * in contiguous ranges of ceil(capacity_rows / n_devices) rows per device (capacity_rows must be > 0), so table order
+ * = shard order and the row ids a search reports are range base + row within the shard; every vector search is one
+ * sema_shard_group_search over a single-process shard group (sema_b200.h: sema_shard_group_create_local): each GPU
+ * scans its range, the shards exchange their top-k over NVLink inside the scan kernel, the call returns the global
+ * top-k.  limit <= 128 for searches on such a store (the reference asks for 50).  n_devices == 1 is sema_store_create. */
+int sema_store_create_multi(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t capacity_rows, int normalize,
+                            sema_store **out);
 int sema_store_destroy(sema_store *st);
 int sema_store_set_embedder(sema_store *st, sema_embed_fn fn, void *user);
 

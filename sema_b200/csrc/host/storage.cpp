@@ -94,16 +94,28 @@ bool like_contains(const std::string &content, const std::string &needle)
 // ------------------------------------------------------------------ GpuVectorIndexer
 GpuVectorIndexer::~GpuVectorIndexer()
 {
-    if (idx_) sema_index_destroy(idx_);
+    if (group_) sema_shard_group_destroy(group_);
+    for (Shard &sh : shards_)
+        if (sh.idx) sema_index_destroy(sh.idx);
 }
 
 Status GpuVectorIndexer::open(int device, uint32_t dim, uint64_t capacity_rows, bool normalize)
 {
-    if (idx_) return Status::Err(SEMA_ERR_INVALID, "indexer already open");
+    return open_multi(&device, 1, dim, capacity_rows, normalize);
+}
+
+Status GpuVectorIndexer::open_multi(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t capacity_rows, bool normalize)
+{
+    if (!shards_.empty()) return Status::Err(SEMA_ERR_INVALID, "indexer already open");
+    if (!devices || n_devices < 1 || n_devices > SEMA_MAX_SHARDS) return Status::Err(SEMA_ERR_INVALID, "between 1 and SEMA_MAX_SHARDS devices");
+    if (n_devices > 1 && capacity_rows == 0)
+        return Status::Err(SEMA_ERR_INVALID, "capacity_rows must be given to split the table over several GPUs");
     // like the reference's table, the index grows as chunks arrive: capacity_rows bounds the address
     // space only (0 = as many rows as 32-bit row ids allow); a driver without virtual memory
     // management gets the fixed-capacity index instead
     const uint64_t max_rows = capacity_rows ? capacity_rows : 0xfffffffeull;
+    const uint64_t per = n_devices == 1 ? max_rows : (capacity_rows + n_devices - 1) / n_devices;
+    if (n_devices > 1 && per * n_devices >= 0xfffffffeull) return Status::Err(SEMA_ERR_INVALID, "capacity_rows above the 32-bit row-id range");
     // Ranking metric.  The reference ranks by LanceDB's default squared-L2 `_distance`
     // (lance_indexer.rs:121-126 sets no distance_type).  With normalize (the reference's own
     // pipeline: every row and query passes through the mean_pool normalise tail) all vectors are
@@ -112,25 +124,82 @@ Status GpuVectorIndexer::open(int device, uint32_t dim, uint64_t capacity_rows, 
     // metric ranks like the reference: the index is then created with SEMA_METRIC_L2 and the
     // score handed out is 1 - d/2 (= the cosine whenever the vectors do happen to be unit-norm).
     metric_ = normalize ? SEMA_METRIC_COSINE : SEMA_METRIC_L2;
-    int rc = sema_index_create_growable(device, dim, max_rows, metric_, &idx_);
-    if (rc == SEMA_ERR_UNSUPPORTED && capacity_rows) rc = sema_index_create(device, dim, capacity_rows, metric_, &idx_);
-    if (rc) return from_rc(rc);
+    Status err = Status::Ok();
+    shards_.resize(n_devices);
+    for (uint32_t g = 0; g < n_devices && err.ok(); ++g) {
+        Shard &sh = shards_[g];
+        sh.base = n_devices == 1 ? 0 : (uint64_t)g * per;
+        sh.cap = per;
+        int rc = sema_index_create_growable(devices[g], dim, per, metric_, &sh.idx);
+        if (rc == SEMA_ERR_UNSUPPORTED && capacity_rows) rc = sema_index_create(devices[g], dim, per, metric_, &sh.idx);
+        if (rc == SEMA_OK && sh.base) rc = sema_index_set_row_base(sh.idx, sh.base);
+        if (rc) { err = from_rc(rc); break; }
+        sema_index_set_normalize_queries(sh.idx, normalize ? 1 : 0);
+    }
+    if (err.ok() && n_devices > 1) {
+        std::vector<sema_index *> ptrs;
+        for (Shard &sh : shards_) ptrs.push_back(sh.idx);
+        const int rc = sema_shard_group_create_local(ptrs.data(), n_devices, &group_);
+        if (rc) err = from_rc(rc);
+    }
+    if (!err.ok()) {
+        for (Shard &sh : shards_)
+            if (sh.idx) sema_index_destroy(sh.idx);
+        shards_.clear();
+        return err;
+    }
+    per_ = per;
     dim_ = dim;
     normalize_ = normalize;
-    sema_index_set_normalize_queries(idx_, normalize ? 1 : 0);
     return Status::Ok();
+}
+
+bool GpuVectorIndexer::locate(uint64_t row, size_t *shard, uint64_t *local) const
+{
+    if (shards_.empty()) return false;
+    const size_t g = shards_.size() == 1 ? 0 : (size_t)(row / per_);
+    if (g >= shards_.size() || row < shards_[g].base) return false;
+    const uint64_t l = row - shards_[g].base;
+    if (l >= shards_[g].chunks.size()) return false;
+    *shard = g;
+    *local = l;
+    return true;
+}
+
+const Chunk *GpuVectorIndexer::chunk(uint64_t row) const
+{
+    size_t g;
+    uint64_t l;
+    return locate(row, &g, &l) ? &shards_[g].chunks[l] : nullptr;
+}
+
+uint64_t GpuVectorIndexer::len() const
+{
+    uint64_t n = 0;
+    for (const Shard &sh : shards_) n += sh.chunks.size();
+    return n;
 }
 
 Status GpuVectorIndexer::index_chunks(const std::vector<Chunk> &chunks, const float *vectors, const uint8_t *valid)
 {
     if (chunks.empty()) return Status::Ok();  // lance_indexer.rs:31-33
-    if (!idx_) return Status::Err(SEMA_ERR_INVALID, "indexer not open");
-    uint64_t first = 0;
-    int rc = sema_index_append(idx_, vectors, chunks.size(), valid, normalize_ ? 1 : 0, &first);
-    if (rc) return from_rc(rc);
-    if (first != chunks_.size()) return Status::Err(SEMA_ERR_INVALID, "row table out of step with the GPU index");
-    chunks_.insert(chunks_.end(), chunks.begin(), chunks.end());
-    live_.insert(live_.end(), chunks.size(), 1);
+    if (shards_.empty()) return Status::Err(SEMA_ERR_INVALID, "indexer not open");
+    // table order = shard order: fill the first shard that still has room, then the next one
+    size_t done = 0;
+    for (Shard &sh : shards_) {
+        if (done == chunks.size()) break;
+        const uint64_t room = sh.cap > sh.chunks.size() ? sh.cap - sh.chunks.size() : 0;
+        if (room == 0) continue;
+        const size_t m = (size_t)std::min<uint64_t>(room, chunks.size() - done);
+        uint64_t first = 0;
+        int rc = sema_index_append(sh.idx, vectors + done * dim_, m, valid ? valid + done : nullptr, normalize_ ? 1 : 0, &first);
+        if (rc) return from_rc(rc);
+        if (first != sh.chunks.size()) return Status::Err(SEMA_ERR_INVALID, "row table out of step with the GPU index");
+        sh.chunks.insert(sh.chunks.end(), chunks.begin() + (std::ptrdiff_t)done, chunks.begin() + (std::ptrdiff_t)(done + m));
+        sh.live.insert(sh.live.end(), m, 1);
+        done += m;
+    }
+    if (done != chunks.size()) return Status::Err(SEMA_ERR_CAPACITY, "the table is full (capacity_rows)");
     return Status::Ok();
 }
 
@@ -156,20 +225,27 @@ Status GpuVectorIndexer::search(const float *q, size_t limit, std::vector<std::p
 {
     out->clear();
     if (rows) rows->clear();
-    if (!idx_) return Status::Ok();  // no table yet => Ok(empty), lance_indexer.rs:108-111
+    if (shards_.empty()) return Status::Ok();  // no table yet => Ok(empty), lance_indexer.rs:108-111
     if (limit > SEMA_MAX_K) return Status::Err(SEMA_ERR_INVALID, "limit above SEMA_MAX_K");
     ids_buf_.resize(limit ? limit : 1);
     sc_buf_.resize(limit ? limit : 1);
     uint32_t nf = 0;
-    int rc = sema_index_search(idx_, q, (uint32_t)limit, ids_buf_.data(), sc_buf_.data(), &nf);
+    int rc;
+    if (group_) {
+        if (limit == 0) return Status::Ok();
+        rc = sema_shard_group_search(group_, q, (uint32_t)limit, ids_buf_.data(), sc_buf_.data(), &nf);
+    } else {
+        rc = sema_index_search(shards_[0].idx, q, (uint32_t)limit, ids_buf_.data(), sc_buf_.data(), &nf);
+    }
     if (rc) return from_rc(rc);
     out->reserve(nf);
     for (uint32_t i = 0; i < nf; ++i) {  // lance_indexer.rs:131-138: rows -> Chunk, in rank order
         const uint64_t row = ids_buf_[i];
-        if (row >= chunks_.size()) return Status::Err(SEMA_ERR_INVALID, "GPU returned a row outside the chunk table");
+        const Chunk *c = chunk(row);
+        if (!c) return Status::Err(SEMA_ERR_INVALID, "GPU returned a row outside the chunk table");
         // the real score (mod.rs:123 attaches 1.0): the cosine, or 1 - d/2 under the literal L2 metric
         const float score = metric_ == SEMA_METRIC_L2 ? 1.0f - 0.5f * sc_buf_[i] : sc_buf_[i];
-        out->emplace_back(chunks_[row], score);
+        out->emplace_back(*c, score);
         if (rows) rows->push_back(row);
     }
     return Status::Ok();
@@ -180,49 +256,56 @@ Status GpuVectorIndexer::search_like(const std::string &query, size_t limit, std
 {
     out->clear();
     if (rows) rows->clear();
-    for (uint64_t r = 0; r < chunks_.size() && out->size() < limit; ++r) {
-        if (!live_[r]) continue;
-        if (like_contains(chunks_[r].content, query)) {
-            out->emplace_back(chunks_[r], 1.0f);  // mod.rs:123
-            if (rows) rows->push_back(r);
+    for (const Shard &sh : shards_)
+        for (uint64_t r = 0; r < sh.chunks.size() && out->size() < limit; ++r) {
+            if (!sh.live[r]) continue;
+            if (like_contains(sh.chunks[r].content, query)) {
+                out->emplace_back(sh.chunks[r], 1.0f);  // mod.rs:123
+                if (rows) rows->push_back(sh.base + r);
+            }
         }
-    }
     return Status::Ok();
 }
 
 Status GpuVectorIndexer::remove_file_chunks(const std::string &file_path, uint64_t *removed)
 {
     if (removed) *removed = 0;
-    if (!idx_) return Status::Ok();  // no table => nothing to delete (lance_indexer.rs:235)
-    std::vector<uint64_t> dead;
-    for (uint64_t r = 0; r < chunks_.size(); ++r)
-        if (live_[r] && chunks_[r].file_path == file_path) dead.push_back(r);
-    if (dead.empty()) return Status::Ok();
-    int rc = sema_index_tombstone(idx_, dead.data(), dead.size());
-    if (rc) return from_rc(rc);
-    for (uint64_t r : dead) live_[r] = 0;
-    if (removed) *removed = dead.size();
+    uint64_t total = 0;
+    for (Shard &sh : shards_) {  // no table => nothing to delete (lance_indexer.rs:235)
+        std::vector<uint64_t> dead;
+        for (uint64_t r = 0; r < sh.chunks.size(); ++r)
+            if (sh.live[r] && sh.chunks[r].file_path == file_path) dead.push_back(r);
+        if (dead.empty()) continue;
+        int rc = sema_index_tombstone(sh.idx, dead.data(), dead.size());
+        if (rc) return from_rc(rc);
+        for (uint64_t r : dead) sh.live[r] = 0;
+        total += dead.size();
+    }
+    if (removed) *removed = total;
     return Status::Ok();
 }
 
 Status GpuVectorIndexer::compact(uint64_t *n_live)
 {
-    if (n_live) *n_live = chunks_.size();
-    if (!idx_ || chunks_.empty()) return Status::Ok();
-    std::vector<uint64_t> map(chunks_.size());
-    uint64_t live = 0;
-    // keep every chunk that was not removed — also those whose embedding failed: they never match a
-    // vector query but the reference's LIKE fallback still finds them
-    int rc = sema_index_compact_keep(idx_, live_.data(), map.data(), &live);
-    if (rc) return from_rc(rc);
-    std::vector<Chunk> kept;
-    kept.reserve(live);
-    for (uint64_t r = 0; r < chunks_.size(); ++r)
-        if (map[r] != ~0ull) kept.push_back(std::move(chunks_[r]));   // the map is order preserving
-    if (kept.size() != live) return Status::Err(SEMA_ERR_INVALID, "compaction map out of step with the chunk table");
-    chunks_ = std::move(kept);
-    live_.assign(chunks_.size(), 1);
-    if (n_live) *n_live = live;
+    uint64_t live_total = 0;
+    for (Shard &sh : shards_) {
+        if (sh.chunks.empty()) continue;
+        std::vector<uint64_t> map(sh.chunks.size());
+        uint64_t live = 0;
+        // keep every chunk that was not removed — also those whose embedding failed: they never match a
+        // vector query but the reference's LIKE fallback still finds them
+        int rc = sema_index_compact_keep(sh.idx, sh.live.data(), map.data(), &live);
+        if (rc) return from_rc(rc);
+        std::vector<Chunk> kept;
+        kept.reserve(live);
+        for (uint64_t r = 0; r < sh.chunks.size(); ++r)
+            if (map[r] != ~0ull) kept.push_back(std::move(sh.chunks[r]));   // the map is order preserving
+        if (kept.size() != live) return Status::Err(SEMA_ERR_INVALID, "compaction map out of step with the chunk table");
+        sh.chunks = std::move(kept);
+        sh.live.assign(sh.chunks.size(), 1);
+        live_total += live;
+    }
+    if (n_live) *n_live = live_total;
     return Status::Ok();
 }
 
@@ -316,6 +399,22 @@ int sema_store_create(int device, uint32_t dim, uint64_t capacity_rows, int norm
     sema_store *st = new (std::nothrow) sema_store();
     if (!st) return store_fail(SEMA_ERR_NOMEM, "host allocation failed");
     Status s = st->mgr.open(device, dim, capacity_rows, normalize != 0);
+    if (!s.ok()) {
+        delete st;
+        return store_fail(s);
+    }
+    *out = st;
+    return SEMA_OK;
+}
+
+int sema_store_create_multi(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t capacity_rows, int normalize,
+                            sema_store **out)
+{
+    if (!out) return store_fail(SEMA_ERR_INVALID, "null out");
+    *out = nullptr;
+    sema_store *st = new (std::nothrow) sema_store();
+    if (!st) return store_fail(SEMA_ERR_NOMEM, "host allocation failed");
+    Status s = st->mgr.open_multi(devices, n_devices, dim, capacity_rows, normalize != 0);
     if (!s.ok()) {
         delete st;
         return store_fail(s);

@@ -71,6 +71,13 @@ public:
 
     // LanceIndexer::new (src/storage/lance_indexer.rs:19-28)
     Status open(int device, uint32_t dim, uint64_t capacity_rows, bool normalize);
+    // The same table over several GPUs of the box, still ONE handle in ONE process like the reference's
+    // StorageManager (src/storage/mod.rs:13-16): the rows are dealt out in contiguous ranges of
+    // ceil(capacity_rows / n) rows per device (table order = shard order), every search is one
+    // sema_shard_group_search over a single-process shard group (sema_shard_group_create_local: each GPU scans its
+    // range, the shards exchange their top-k over NVLink inside the scan kernel, the call returns the global
+    // top-k).  capacity_rows must be given (> 0) when n_devices > 1; limit <= 128 for searches then.
+    Status open_multi(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t capacity_rows, bool normalize);
 
     // index_chunks (:30-105).  `vectors`: chunks.size() x dim; valid[i] == 0 marks a failed
     // embedding (null vector).  Empty input is Ok (:31-33).
@@ -91,18 +98,28 @@ public:
     // table to match (row ids returned by later searches refer to the compacted table)
     Status compact(uint64_t *n_live = nullptr);
 
-    const Chunk *chunk(uint64_t row) const { return row < chunks_.size() ? &chunks_[row] : nullptr; }
-    uint64_t len() const { return chunks_.size(); }
+    // row = the id a search reports: shard base + row within the shard (one shard: simply the table row)
+    const Chunk *chunk(uint64_t row) const;
+    uint64_t len() const;                                  // chunks in the table (all shards)
     uint32_t dim() const { return dim_; }
-    sema_index *index() { return idx_; }
+    uint32_t n_shards() const { return (uint32_t)shards_.size(); }
+    sema_index *index() { return shards_.empty() ? nullptr : shards_[0].idx; }   // shard 0's index (the only one on one GPU)
 
 private:
-    sema_index *idx_ = nullptr;
+    struct Shard {
+        sema_index *idx = nullptr;
+        uint64_t base = 0;            // global id of its row 0 (sema_index_set_row_base)
+        uint64_t cap = 0;             // rows it may hold
+        std::vector<Chunk> chunks;    // row -> Chunk (extract_chunk_from_batch, :252-281)
+        std::vector<uint8_t> live;    // 0 after remove_file_chunks
+    };
+    bool locate(uint64_t row, size_t *shard, uint64_t *local) const;
+    std::vector<Shard> shards_;
+    sema_shard_group *group_ = nullptr;   // single-process shard group over the shards (more than one GPU only)
+    uint64_t per_ = 0;                    // rows per shard range (more than one GPU only)
     uint32_t dim_ = 0;
     bool normalize_ = false;
     int metric_ = SEMA_METRIC_COSINE;   // SEMA_METRIC_L2 when the caller's vectors are stored as given (normalize = false)
-    std::vector<Chunk> chunks_;   // row -> Chunk (extract_chunk_from_batch, :252-281)
-    std::vector<uint8_t> live_;   // 0 after remove_file_chunks
     std::vector<uint64_t> ids_buf_;
     std::vector<float> sc_buf_;
 };
@@ -113,6 +130,10 @@ public:
     Status open(int device, uint32_t dim, uint64_t capacity_rows, bool normalize)
     {
         return lance_indexer.open(device, dim, capacity_rows, normalize);
+    }
+    Status open_multi(const int *devices, uint32_t n_devices, uint32_t dim, uint64_t capacity_rows, bool normalize)
+    {
+        return lance_indexer.open_multi(devices, n_devices, dim, capacity_rows, normalize);
     }
     void set_embedder(Embedder e) { embedder_ = std::move(e); }
 

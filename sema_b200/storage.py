@@ -50,6 +50,7 @@ _cpp = C.POINTER(C.c_char_p)
 _u64p = C.POINTER(C.c_uint64)
 STORE_SIGNATURES = {
     "sema_store_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(_vp)]),
+    "sema_store_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "sema_store_destroy": (C.c_int, [_vp]),
     "sema_store_set_embedder": (C.c_int, [_vp, EMBED_FN, _vp]),
     "sema_store_index_chunks": (C.c_int, [_vp, C.c_uint64, _cpp, _cpp, _u64p, _u64p, _cpp, _vp, _vp]),
@@ -119,10 +120,18 @@ class StorageManager:
     """``StorageManager`` (src/storage/mod.rs:13-132), vector route, on one GPU."""
 
     def __init__(self, dim: int = 384, capacity_rows: int = 1 << 20, device: int = 0, normalize: bool = True,
-                 embedder=None):
+                 embedder=None, devices=None):
+        """devices: a list of GPU ordinals spreads the table over them (one process, one handle: the rows are dealt
+        out in contiguous ranges of capacity_rows / len(devices), every search is one fused multi-GPU scan)."""
         self._lib = _L()
         self._h = _vp()
-        _check(self._lib.sema_store_create(device, dim, capacity_rows, int(normalize), C.byref(self._h)))
+        if devices is not None and len(devices) > 1:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(self._lib.sema_store_create_multi(arr, len(devices), dim, capacity_rows, int(normalize), C.byref(self._h)))
+        else:
+            if devices:
+                device = int(devices[0])
+            _check(self._lib.sema_store_create(device, dim, capacity_rows, int(normalize), C.byref(self._h)))
         self.dim = dim
         self._cb = None
         if embedder is not None:

@@ -174,3 +174,71 @@ def test_store_without_normalisation_ranks_by_l2_like_the_reference(oracle_c):
     assert np.array_equal(got_rows, l2_ids)                                 # gaps between distances are >> 1e-5 here
     np.testing.assert_allclose([s for _, s in got], 1.0 - 0.5 * l2_d, rtol=1e-5, atol=1e-5)
     assert [c.id for c, _ in via_text] == [c.id for c, _ in got]
+
+
+def _all_devices():
+    from sema_b200 import _lib
+    return list(range(min(int(_lib.lib().sema_device_count()), 8)))
+
+
+def test_multi_gpu_store_equals_single_gpu_store_and_oracle():
+    """sema_store_create_multi: ONE StorageManager handle in ONE process over every visible GPU (the reference is one
+    process with one StorageManager).  Runs with however many GPUs the box shows — on a 1-GPU box it is the single-device
+    store again; `gpurun --gpus N` exercises the contiguous row ranges, the fused peer exchange behind every search,
+    per-shard tombstones, per-shard compaction and the table-order LIKE scan across shards."""
+    from sema_b200.storage import Chunk, StorageManager
+    devs = _all_devices()
+    files = corpus.make_markdown_tree(260, seed=9)
+    raw = corpus.chunk_tree(files)
+    chunks = [Chunk(c["id"], c["file_path"], c["start_line"], c["end_line"], c["content"]) for c in raw]
+    emb = np.stack([corpus.embed(c.content) for c in chunks])
+    X = O.normalize(emb)
+    n = len(chunks)
+    row_of = {c.id: i for i, c in enumerate(chunks)}
+    with StorageManager(dim=corpus.DIM, capacity_rows=n + 3, normalize=True, embedder=corpus.embed, devices=devs) as mgr, \
+         StorageManager(dim=corpus.DIM, capacity_rows=n + 3, normalize=True, embedder=corpus.embed) as one:
+        third = n // 3
+        for m in (mgr, one):                                   # three batches: ranges fill in table order, batches straddle shards
+            m.index_chunks(chunks[:third], vectors=emb[:third])
+            m.index_chunks(chunks[third:2 * third])
+            m.index_chunks(chunks[2 * third:], vectors=emb[2 * third:])
+            assert len(m) == n
+        rng = np.random.default_rng(21)
+        for _ in range(40):
+            words = " ".join(corpus._WORDS[int(i)] for i in rng.integers(0, len(corpus._WORDS), 5))
+            got = mgr.search(words, 50)
+            ref = one.search(words, 50)
+            assert [c.id for c, _ in got] == [c.id for c, _ in ref]
+            assert [s for _, s in got] == [s for _, s in ref]                  # same kernels, same bits
+            r_ids, r_sc = O.scan(X, O.normalize(corpus.embed(words)), 50)
+            O.check_parity(np.array([row_of[c.id] for c, _ in got], dtype=np.uint64),
+                           np.array([s for _, s in got], dtype=np.float32), r_ids, r_sc)
+        q = "storage engine table row column"
+        assert [g.chunk.id for g in mgr.execute_search(q)] == [g.chunk.id for g in one.execute_search(q)]
+        assert [c.id for c, _ in mgr.search("## ", 30)] == [c.id for c, _ in one.search("## ", 30)]   # LIKE: table order
+        # remove the files of the first ten hits (they live on different shards), then compact
+        victims = sorted({c.file_path for c, _ in mgr.search(q, 10)})
+        for v in victims:
+            assert mgr.remove_file_chunks(v) == one.remove_file_chunks(v) > 0
+        after = mgr.search(q, 50)
+        assert all(c.file_path not in victims for c, _ in after)
+        assert [c.id for c, _ in after] == [c.id for c, _ in one.search(q, 50)]
+        live = mgr.compact()
+        assert live == one.compact() == sum(1 for c in chunks if c.file_path not in victims) == len(mgr)
+        assert [c.id for c, _ in mgr.search(q, 50)] == [c.id for c, _ in after]
+        assert [c.id for c, _ in mgr.search("## ", 30)] == [c.id for c, _ in one.search("## ", 30)]
+        more = [Chunk(f"new.md:{i}", "new.md", i + 1, i + 1, "tensor shard merge bandwidth kernel") for i in range(5)]
+        mgr.index_chunks(more)                                 # appends land in the first range with room
+        assert any(c.file_path == "new.md" for c, _ in mgr.search("tensor shard merge bandwidth kernel", 10))
+
+
+def test_multi_gpu_store_argument_checks():
+    from sema_b200 import SemaError
+    from sema_b200.storage import StorageManager
+    devs = _all_devices()
+    if len(devs) < 2:
+        pytest.skip("needs two GPUs")
+    with pytest.raises(SemaError):
+        StorageManager(dim=corpus.DIM, capacity_rows=0, devices=devs)          # ranges need a capacity
+    with pytest.raises(SemaError):
+        StorageManager(dim=corpus.DIM, capacity_rows=100, devices=[0, 0])      # one shard per device
