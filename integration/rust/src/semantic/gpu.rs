@@ -29,7 +29,18 @@ extern "C" {
     fn sema_index_size(idx: *const SemaIndex) -> u64;
     fn sema_index_save(idx: *mut SemaIndex, path: *const c_char) -> c_int;
     fn sema_index_load(path: *const c_char, device: c_int, capacity_rows: u64, out: *mut *mut SemaIndex) -> c_int;
+    fn sema_index_set_row_base(idx: *mut SemaIndex, row_base: u64) -> c_int;
+    fn sema_device_count() -> c_int;
+    fn sema_shard_group_create_local(shards: *const *mut SemaIndex, n_shards: u32, out: *mut *mut SemaShardGroup) -> c_int;
+    fn sema_shard_group_search(g: *mut SemaShardGroup, q: *const f32, k: u32, row_ids: *mut u64, scores: *mut f32,
+                               n_found: *mut u32) -> c_int;
+    fn sema_shard_group_destroy(g: *mut SemaShardGroup) -> c_int;
     fn sema_last_error() -> *const c_char;
+}
+
+#[repr(C)]
+pub struct SemaShardGroup {
+    _private: [u8; 0],
 }
 
 fn check(rc: c_int) -> anyhow::Result<()> {
@@ -126,5 +137,71 @@ impl GpuIndex {
 impl Drop for GpuIndex {
     fn drop(&mut self) {
         unsafe { sema_index_destroy(self.raw) };
+    }
+}
+
+/// The same index spread over every GPU of the box behind ONE handle (Sema is one process with one
+/// StorageManager: src/main.rs:9, src/storage/mod.rs:13-16).  Rows are dealt out in contiguous ranges of
+/// `capacity_rows / n_gpus`; a search is one host call: every GPU scans its range, the shards exchange their
+/// top-k over NVLink inside the scan kernel, the call returns the global top-k (limit <= 128).
+pub struct MultiGpuIndex {
+    shards: Vec<GpuIndex>,
+    group: *mut SemaShardGroup,
+    per: u64,
+    dim: usize,
+}
+
+unsafe impl Send for MultiGpuIndex {}
+
+impl MultiGpuIndex {
+    pub fn new(dim: usize, capacity_rows: u64) -> anyhow::Result<Self> {
+        let n = unsafe { sema_device_count() }.max(1) as u64;
+        let per = (capacity_rows + n - 1) / n;
+        let mut shards = Vec::new();
+        for g in 0..n {
+            let shard = GpuIndex::new(g as i32, dim, per)?;
+            check(unsafe { sema_index_set_row_base(shard.raw, g * per) })?;
+            shards.push(shard);
+        }
+        let raws: Vec<*mut SemaIndex> = shards.iter().map(|s| s.raw).collect();
+        let mut group = std::ptr::null_mut();
+        check(unsafe { sema_shard_group_create_local(raws.as_ptr(), raws.len() as u32, &mut group) })?;
+        Ok(Self { shards, group, per, dim })
+    }
+
+    /// Appends fill the ranges in table order; returns the global id of the first appended row.
+    pub fn append(&mut self, rows: &[f32], valid: &[u8], normalize: bool) -> anyhow::Result<u64> {
+        let n = rows.len() / self.dim;
+        let (mut done, mut first_global) = (0usize, None);
+        for (g, shard) in self.shards.iter_mut().enumerate() {
+            if done == n {
+                break;
+            }
+            let room = (self.per - shard.len()) as usize;
+            let m = room.min(n - done);
+            if m == 0 {
+                continue;
+            }
+            let v = if valid.is_empty() { &valid[..] } else { &valid[done..done + m] };
+            let local = shard.append(&rows[done * self.dim..(done + m) * self.dim], v, normalize)?;
+            first_global.get_or_insert(g as u64 * self.per + local);
+            done += m;
+        }
+        anyhow::ensure!(done == n, "the index is full");
+        Ok(first_global.unwrap_or(0))
+    }
+
+    /// Ranked (global row, cosine) pairs, best first.
+    pub fn search(&mut self, q: &[f32], limit: usize) -> anyhow::Result<Vec<(u64, f32)>> {
+        anyhow::ensure!(q.len() == self.dim, "query has {} dims, index has {}", q.len(), self.dim);
+        let (mut ids, mut sc, mut nf) = (vec![0u64; limit.max(1)], vec![0f32; limit.max(1)], 0u32);
+        check(unsafe { sema_shard_group_search(self.group, q.as_ptr(), limit as u32, ids.as_mut_ptr(), sc.as_mut_ptr(), &mut nf) })?;
+        Ok(ids.into_iter().zip(sc).take(nf as usize).collect())
+    }
+}
+
+impl Drop for MultiGpuIndex {
+    fn drop(&mut self) {
+        unsafe { sema_shard_group_destroy(self.group) };   // before the shards it refers to
     }
 }
