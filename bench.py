@@ -800,7 +800,9 @@ def run_ours(a):
 
         # ---- end-to-end region: host query in, host results out, through the public call.  The clock sampler keeps
         # running but ten times less often: NVML queries take driver locks, and a host-driven loop of 2 ms calls is
-        # exposed to that where a pre-enqueued device stream is not (the spread of this region is reported in `repeats`)
+        # exposed to that where a pre-enqueued device stream is not (on the power-capped boxes of this pool the five
+        # repeats read 2.13 - 2.29 ms per call with a sample every 20 ms and 2.062 - 2.066 ms with one every 200 ms;
+        # the spread of this region is reported in `repeats`)
         clk.period = 0.2
         e2e_all, e2e_lat, e2e_pipe_ms = [], None, None
         if a.staged_host_path:
