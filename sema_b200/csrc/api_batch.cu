@@ -1,4 +1,5 @@
-// api_batch.cu — K3: bf16 planes, cluster launch, exact re-scoring, K2 fallback; batched entry points.
+// api_batch.cu — K3: 16-bit hi/lo planes (fp16 or bf16), cluster launches (mixed cluster sizes, CTA-pair variant),
+// exact re-scoring, cascade and K2 fallback; batched entry points.
 #include "index_impl.cuh"
 #include "k3_batch.cuh"
 #include "k3_pair.cuh"

@@ -5,24 +5,25 @@
 // contraction S = Q . X^T (Q x N x d), so this path runs it on the 5th-gen tensor
 // cores with error-compensated split precision and a fused per-query selection:
 //
-//   x = x_hi + x_lo, q = q_hi + q_lo (bf16 each, round-to-nearest residuals)
+//   x = x_hi + x_lo, q = q_hi + q_lo (16-bit halves, round-to-nearest residuals: fp16 when every stored element is
+//   <= 1024 in magnitude — unit roundoff u = 2^-11 — else bf16, u = 2^-8; Params::fmt)
 //   S ~= q_hi.x_hi + q_lo.x_hi + q_hi.x_lo     (3 x kind::f16 UMMA, fp32 accumulate in TMEM)
-//   |S - q.x| <= 3*2^-16 |q||x| + fp32 accumulation error  (dropped terms are O(2^-16))
+//   |S - q.x| <= 3 u^2 |q||x| + fp32 accumulation error;  one pass (q_hi.x_hi): <= (2u + u^2) |q||x| + accumulation
 //
-// The tensor-core pass only *selects* candidates (KC >= k per query and row partition);
-// k3_rescore_kernel then recomputes the candidates' scores in plain fp32 with K2's
+// The tensor-core pass only *selects* candidates (a short list per query and row partition);
+// rescore_kernel then recomputes the surviving candidates' scores in plain fp32 with K2's
 // arithmetic, ranks them exactly and proves, per query, that no row outside the candidate
-// lists can reach the k-th exact score (else the query is flagged and the host re-runs it
-// through K2).  Results are therefore exactly K2's.
+// lists can reach the k-th exact score (else the query is flagged and the host sends it to the
+// next stage of the cascade / through K2).  Results are therefore exactly K2's.
 //
 // Layout.  A CTA owns one tile of 128 queries — the UMMA A operand, kept resident in
-// TMEM for the CTA's lifetime (row m <-> TMEM lane m, 2 bf16 per 32-bit column: q_hi in
+// TMEM for the CTA's lifetime (row m <-> TMEM lane m, 2 halves per 32-bit column: q_hi in
 // columns [0,192), q_lo in [192,384) for d = 384) — and streams a contiguous range of
 // 64-row corpus tiles (the B operand) through a shared-memory ring with 1-D bulk async
 // copies (TMA, cp.async.bulk + mbarrier complete_tx).  The corpus planes are stored in
 // HBM already in the UMMA canonical K-major no-swizzle core-matrix order, so a stage is
 // one contiguous 16 KB copy and needs no tensor map: per 64-row tile, per 64-wide k
-// block: [hi | lo][k-chunk of 8 elements (8)][row group (8)][row in group (8)][8 bf16].
+// block: [hi | lo][k-chunk of 8 elements (8)][row group (8)][row in group (8)][8 halves].
 // Two 128x64 fp32 accumulators (TMEM columns [384,448) and [448,512)) double-buffer the
 // MMA against the epilogue.  Each epilogue thread owns one query (= one TMEM lane): it
 // reads its 64 scores with tcgen05.ld and keeps a private candidate list in shared memory.
