@@ -78,6 +78,8 @@ def parse():
     ap.add_argument("--growable", action="store_true", help="corpus in a growable (virtual-memory backed) index")
     ap.add_argument("--no-stream", action="store_true", help="timed region: one search call per query instead of one query stream")
     ap.add_argument("--no-chain", action="store_true", help="query stream without programmatic dependent launch (comparison)")
+    ap.add_argument("--launch-per-query", action="store_true",
+                    help="query stream as one K2 launch per query instead of one persistent launch (comparison)")
     ap.add_argument("--staged-host-path", action="store_true", help="e2e through the staged H2D / D2H path (comparison)")
     return ap.parse_args()
 
@@ -740,6 +742,8 @@ def run_ours(a):
     nf_s = torch.zeros(n_s, dtype=torch.int32, device=dev)
     if a.no_chain:
         idx.set_scan_variant(600)
+    if a.no_chain or a.launch_per_query:
+        idx.set_scan_variant(902)
     searcher = idx if world == 1 else group
 
     def run_device(nq):
@@ -924,11 +928,20 @@ def run_ours(a):
                 traffic = tr.get(f"k2_single_{a.rows}x{a.dim}")
         except Exception:
             pass
-        kern = "scan_topk_tma_kernel (K2, TMA ring)" if (a.variant <= 0 and a.dim in (384, 768)) else "scan_topk_kernel (K2, register-fed)"
+        # one persistent launch for the whole region (k2_stream.cuh) when the library chose it: launches < steps
+        persistent = bool(use_stream and launches < a.steps)
+        kern = ("scan_stream_kernel (K2, TMA ring, one persistent launch per query stream)" if persistent
+                else "scan_topk_tma_kernel (K2, TMA ring)" if (a.variant <= 0 and a.dim in (384, 768)) else "scan_topk_kernel (K2, register-fed)")
         roof = hbm_roofline(shard_rows, a.dim, dev_ms, kern, traffic)
-        roof["traffic_source"] = "profiles/r01_k2_scan_full_raw.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum)" if traffic else None
-        roof["note"] = ("achieved = rows_per_gpu*dim*4 bytes / device time per step (one K2 launch per step"
-                        + ("" if world == 1 else ", which includes the top-k exchange and the global merge") + ")")
+        roof["traffic_source"] = "profiles/r01_k2_scan_full_raw.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum; per pass over the corpus)" if traffic else None
+        tail = "" if world == 1 else ", which includes the top-k exchange and the global merge"
+        if persistent:
+            roof["passes_per_launch"] = a.steps
+            roof["algorithmic_bytes_per_launch"] = int(shard_rows) * a.dim * 4 * a.steps
+            roof["note"] = (f"ONE K2 launch scans the corpus once per step ({a.steps} passes per launch): achieved = "
+                            "passes * rows_per_gpu*dim*4 bytes / launch duration = rows_per_gpu*dim*4 / device time per step" + tail)
+        else:
+            roof["note"] = "achieved = rows_per_gpu*dim*4 bytes / device time per step (one K2 launch per step" + tail + ")"
         all_ok = all(x is not False for x in (verified, stream_consistent)) and not oracle_fail
         line = {
             "metric": metric_name(a.rows, a.dim, a.k), "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
@@ -940,7 +953,9 @@ def run_ours(a):
                 "parallelism": "single GPU" if world == 1 else f"corpus row-sharded over {world} GPUs (one process each)",
                 "exchange": exchange if world > 1 else None,
                 "issue": ("one query stream of K queries (sema_index_search_stream_device / sema_shard_group_search_stream_device): "
-                          "one K2 launch per query, " + ("unchained" if a.no_chain else "consecutive launches chained with programmatic dependent launch"))
+                          + ("ONE persistent K2 launch for the stream — the producer warp streams query i+1's rows while a finisher warp "
+                             "merges, exchanges and publishes query i (gpu_launches counts launches, not passes)" if persistent else
+                             "one K2 launch per query, " + ("unchained" if a.no_chain else "consecutive launches chained with programmatic dependent launch")))
                          if use_stream else "one search call per query",
                 "timing": "CUDA events on the launching stream, barrier + synchronize both sides, max over ranks; "
                           f"the region of exactly {a.steps} steps is timed {reps} times, value = median",

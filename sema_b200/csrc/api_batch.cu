@@ -616,6 +616,14 @@ int scan_stream(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_
                              nq, cudaMemcpyDeviceToDevice, s->stream));
         Qp = s->Qpad_dev;
     }
+    if (stream_kernel_ok(s, nq, n, k)) {
+        if (x) x->seq = *seq + 1;  // query i exchanges under sequence number *seq + 1 + i, as the launch-per-query form does
+        const int rc = stream_kernel_launch(s, Qp, nq, n, k, ids_d, sc_d, nf_d, x);
+        if (rc != STREAM_FALLBACK) {
+            if (x && rc == SEMA_OK) *seq += nq;
+            return rc;
+        }
+    }
     for (uint32_t i = 0; i < nq; ++i) {
         if (x) x->seq = ++*seq;
         const unsigned flags = (i > 0 && s->chain) ? SCAN_CHAINED : 0u;

@@ -232,6 +232,8 @@ static int create_impl(int device, uint32_t dim, uint64_t capacity_rows, int met
     CKD(cudaMalloc(&s->partials, (size_t)s->num_sms * MAX_BLOCKS_PER_SM * K_PASS * sizeof(uint64_t)));
     CKD(cudaMalloc(&s->ticket, 4 * sizeof(unsigned int)));
     CKD(cudaMemset(s->ticket, 0, 4 * sizeof(unsigned int)));
+    CKD(cudaMalloc(&s->stream_ctl, STREAM_CTL_WORDS * sizeof(unsigned int)));
+    CKD(cudaMemset(s->stream_ctl, 0, STREAM_CTL_WORDS * sizeof(unsigned int)));
     CKD(cudaMalloc(&s->keys_dev, SEMA_MAX_K * sizeof(uint64_t)));
     CKD(cudaMalloc(&s->max_norm2, 2 * sizeof(float)));
     CKD(cudaMalloc(&s->qscratch, 65536 + 32));
@@ -263,7 +265,7 @@ int sema_index_destroy(sema_index *s)
         s->X = nullptr; s->valid = nullptr; s->planes = nullptr;
     }
     cudaFree(s->X); cudaFree(s->valid); cudaFree(s->q_dev); cudaFreeHost(s->q_pin);
-    cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->keys_dev); cudaFree(s->res_dev);
+    cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->stream_ctl); cudaFree(s->keys_dev); cudaFree(s->res_dev);
     cudaFreeHost(s->res_pin); cudaFreeHost(s->res_map); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
     cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
     cudaFree(s->qscratch); cudaFree(s->max_norm2); cudaFree(s->planes); cudaFree(s->Qpad_dev); cudaFree(s->cand_rows);
@@ -669,6 +671,8 @@ int sema_index_set_scan_variant(sema_index *s, int variant)
     if (variant >= 1102) return -1;
     if (variant >= 1100) { s->k3_mixed = variant - 1100; return variant; }   // 1100 / 1101 = a K3 stage as one launch / as two concurrent launches (clusters of 4 + clusters of 2, default)
     if (variant >= 1000) return -1;
+    if (variant >= 903) return -1;
+    if (variant >= 900) { s->stream_mode = variant - 900; return variant; }  // query streams: 900 = one persistent launch when a scan is long enough (default), 901 = whenever the shape allows, 902 = one launch per query
     if (variant >= 800) { s->k3_prefetch = variant - 800; return variant; }  // 800 + d = K3 producer prefetches into L2 d stages ahead (0 = off)
     if (variant >= 702) return -1;
     if (variant >= 700) { s->k3_pair = variant - 700; return variant; }      // 700 = single-CTA kernel for the single-pass stage (default), 701 = CTA pairs (tcgen05 cta_group::2)

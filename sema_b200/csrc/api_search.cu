@@ -3,6 +3,7 @@
 #include "k2_scan.cuh"
 #include "k4_merge.cuh"
 #include "k2_scan_tma.cuh"
+#include "k2_stream.cuh"
 
 using namespace sema;
 using namespace sema_impl;
@@ -178,6 +179,86 @@ int scan_pass(sema_index *s, const ScanArgs &a)
     return s->metric == SEMA_METRIC_L2 ? scan_shape<METRIC_L2>(s, a) : scan_shape<METRIC_COSINE>(s, a);
 }
 
+// ---- K2 for a whole query stream in ONE persistent launch (k2_stream.cuh) ----
+constexpr int STREAM_REFUSED = 1;   // internal: the cooperative launch was refused, nothing was launched
+struct StreamArgs {
+    const float *Q;      // nq x ld floats, device, 16-byte aligned
+    uint32_t nq, n, k;
+    uint64_t *ids;
+    float *sc;
+    uint32_t *nf;
+    const Exchange *x;   // x->seq = sequence number of query 0
+};
+
+template <int NV, int M, int METRIC>
+int run_stream(sema_index *s, const StreamArgs &a)
+{
+    auto kern = scan_stream_kernel<NV, M, METRIC>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[s->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, stream_smem_bytes<NV, M>()));
+        attr_set[s->device & 63] = true;
+    }
+    const uint32_t n_tiles = (a.n + stream_tile_rows<NV>() - 1) / stream_tile_rows<NV>();
+    uint32_t grid = (uint32_t)s->num_sms;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    static_assert(2 * 32 * 4 <= MAX_BLOCKS_PER_SM * K_PASS, "two parities of block lists fit the partials buffer");
+    StreamParams p;
+    p.X = reinterpret_cast<const float4 *>(s->X);
+    p.Q = a.Q;
+    p.partials = s->partials;
+    p.work_ctr = reinterpret_cast<unsigned long long *>(s->stream_ctl);
+    p.done = s->stream_ctl + 2;
+    p.fault = s->stream_ctl + 3;
+    p.ticket = s->stream_ctl + 4;
+    p.res_ids = a.ids;
+    p.res_scores = a.sc;
+    p.res_nfound = a.nf;
+    p.n = a.n;
+    p.ld4 = s->ld / 4;
+    p.k = a.k;
+    p.row_base = s->row_base;
+    p.nq = a.nq;
+    if (a.x) p.x = *a.x;
+    else memset(&p.x, 0, sizeof p.x);
+    CK(cudaMemsetAsync(s->stream_ctl, 0, STREAM_CTL_WORDS * sizeof(unsigned int), s->stream));
+    // The blocks wait for each other (done, tickets), so all of them must be resident at once: a cooperative launch
+    // guarantees that or is refused (SM partitioning, MPS limits) — then the caller falls back to one launch per query.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(STREAM_THREADS);
+    cfg.dynamicSmemBytes = stream_smem_bytes<NV, M>();
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported) {
+        (void)cudaGetLastError();
+        return STREAM_REFUSED;
+    }
+    CK(e);
+    s->launches++;
+    return SEMA_OK;
+}
+
+template <int NV, int METRIC>
+int stream_m(sema_index *s, const StreamArgs &a)
+{
+    if (a.k <= 32) return run_stream<NV, 1, METRIC>(s, a);
+    if (a.k <= 64) return run_stream<NV, 2, METRIC>(s, a);
+    return run_stream<NV, 4, METRIC>(s, a);
+}
+
+template <int METRIC>
+int stream_shape(sema_index *s, const StreamArgs &a)
+{
+    return s->ld / 4 == 96 ? stream_m<3, METRIC>(s, a) : stream_m<6, METRIC>(s, a);
+}
+
 template <int METRIC>
 int merge_pass_m(sema_index *s, const uint64_t *keys, uint32_t total, uint32_t k,
                  const uint64_t *bound, uint64_t *out_keys, uint64_t *ids, float *sc, uint32_t *nf)
@@ -230,6 +311,32 @@ int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64
     }
     if (res_ids) return decode(s, keys, k, res_ids, res_scores, res_nfound);
     return SEMA_OK;
+}
+
+// One persistent launch for the whole stream?  Shapes of the TMA kernel only; by default only when one scan is long
+// against the finisher warp's per-query work (block merge + the last block's merge over all blocks: a few us for
+// k <= 16, tens of us for k = 100), so short scans keep the chained launches that finish a query on eight warps.
+bool stream_kernel_ok(const sema_index *s, uint32_t nq, uint32_t n, uint32_t k)
+{
+    const uint32_t ld4 = s->ld / 4;
+    if (s->stream_mode == 2 || s->variant != 0 || nq < 2 || k < 1 || k > (uint32_t)K_PASS) return false;
+    if (s->ld != s->dim || (ld4 != 96 && ld4 != 192)) return false;
+    if (s->stream_mode == 1) return true;
+    const uint64_t floats = (uint64_t)n * s->ld;
+    return floats >= (k <= 16 ? 38000000ull : 300000000ull);    // ~20 us / ~160 us of scan at 7.4 TB/s (measured: 100 k x 384 rows at k = 10 gain 8 %)
+}
+
+int stream_kernel_launch(sema_index *s, const float *Q, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+                         uint32_t *nf_d, const Exchange *x)
+{
+    SEMA_NVTX("sema.K2.stream");
+    const StreamArgs a{Q, nq, n, k, ids_d, sc_d, nf_d, x};
+    const int rc = s->metric == SEMA_METRIC_L2 ? stream_shape<METRIC_L2>(s, a) : stream_shape<METRIC_COSINE>(s, a);
+    if (rc == STREAM_REFUSED) {
+        s->stream_mode = 2;      // this device / context cannot hold the whole grid at once: do not try again
+        return STREAM_FALLBACK;
+    }
+    return rc;
 }
 
 bool host_query_ok(const sema_index *s, uint32_t k)

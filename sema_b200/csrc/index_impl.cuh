@@ -66,6 +66,8 @@ constexpr int RES_SLOTS = SEMA_MAX_INFLIGHT;
 constexpr size_t RES_SLOT_BYTES = 4096;
 constexpr size_t RES_MAP_BYTES = RES_SLOTS * RES_SLOT_BYTES;
 constexpr size_t RES_MAP_FLAG_OFF = 2048;
+constexpr int STREAM_FALLBACK = 0x5eaa;   // stream_kernel_launch: the cooperative launch was refused; issue the stream one launch per query
+constexpr int STREAM_CTL_WORDS = 8;   // persistent stream kernel: [0,1] work counter (u64), [2] done, [3] fault, [4,5] tickets
 
 }  // namespace sema_impl
 
@@ -91,6 +93,8 @@ struct sema_index {
     uint64_t *partials = nullptr;     // num_sms * MAX_BLOCKS_PER_SM * 128 keys
     unsigned int *ticket = nullptr;   // [0] arrival ticket, [2], [3] tile-claim counters of the TMA scan (alternating)
     uint64_t scan_seq = 0;            // TMA scans launched (selects the claim counter)
+    unsigned int *stream_ctl = nullptr;   // control words of the persistent stream kernel (STREAM_CTL_WORDS), zeroed before every launch
+    int stream_mode = 0;              // query streams: 0 = one persistent launch when a scan is long enough, 1 = whenever the shape allows, 2 = always one launch per query
     unsigned char *res_map = nullptr; // mapped pinned host memory the host-query path writes results to (RES_MAP_BYTES)
     unsigned char *res_map_dev = nullptr;   // its device address
     uint64_t host_seq = 0;            // tickets issued so far; ticket t uses slot t % RES_SLOTS and stores t to its flag
@@ -201,8 +205,12 @@ int k3_poison_rows(sema_index *s, const uint64_t *rows_dev, uint64_t n);
 // api_batch.cu: nq device-resident queries (nq x dim dense); K3 when the shape allows, else K2 per query
 int batch_core(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
                uint32_t *nf_d);
-// api_batch.cu: a stream of nq single-query scans (K2 each), consecutive launches chained (PDL);
-// x / seq: optional fused shard exchange, *seq advanced once per query
+// api_search.cu: the whole stream as ONE persistent launch (k2_stream.cuh); x->seq = sequence number of query 0
+bool stream_kernel_ok(const sema_index *s, uint32_t nq, uint32_t n, uint32_t k);
+int stream_kernel_launch(sema_index *s, const float *Q, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
+                         uint32_t *nf_d, const sema::Exchange *x);
+// api_batch.cu: a stream of nq single-query scans (K2): one persistent launch, or one launch per query with
+// consecutive launches chained (PDL); x / seq: optional fused shard exchange, *seq advanced once per query
 int scan_stream(sema_index *s, const float *Qd, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
                 uint32_t *nf_d, sema::Exchange *x, uint64_t *seq);
 

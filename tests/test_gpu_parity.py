@@ -1191,6 +1191,95 @@ def test_shard_group_stream_world1(sema, oracle_c):
             g.close()
 
 
+# ---- the whole stream as ONE persistent launch (k2_stream.cuh): producer never drains, finisher warp merges
+PERSISTENT_CASES = [
+    # n, d, k, nq, metric — tiny corpora (fewer tiles than blocks, blocks that see no tile of a query), both dims,
+    # every list width (k <= 16 by selection rounds, M = 1 / 2 / 4 by bitonic merges), odd and even query counts
+    (1, 384, 10, 3, 0), (31, 384, 10, 5, 0), (33, 384, 50, 7, 1), (4737, 384, 10, 40, 0), (4737, 768, 100, 9, 0),
+    (150001, 384, 10, 64, 0), (150001, 384, 128, 6, 1), (60000, 768, 10, 33, 0), (20000, 384, 16, 2, 0),
+    (20000, 384, 17, 11, 0), (9000, 768, 64, 5, 1),
+]
+
+
+@pytest.mark.parametrize("n,d,k,nq,metric", PERSISTENT_CASES)
+def test_persistent_stream_matches_oracle_and_single_calls(sema, oracle_c, n, d, k, nq, metric):
+    X = _unit(1, n, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n, metric=metric) as idx:
+        idx.append(X, normalize=False)
+        assert idx.set_scan_variant(901) == 901          # one persistent launch whatever the corpus size
+        before = idx.launch_count
+        ids, sc, nf = _stream_search(sema, idx, Q, k)
+        assert idx.launch_count - before == 1
+        for i in range(nq):
+            r_ids, r_sc = oracle_c.scan(X, Q[i], k, metric)
+            assert nf[i] == len(r_ids) == min(k, n)
+            O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+            one_ids, one_sc = idx.search(Q[i], k)
+            assert np.array_equal(one_ids, ids[i, :nf[i]]) and np.array_equal(one_sc, sc[i, :nf[i]])
+
+
+def test_persistent_stream_equals_launch_per_query_bitwise(sema):
+    # 300 007 rows x 384: by default k = 10 streams take the persistent launch (a scan is long against the finisher
+    # warp's work), k = 50 streams need a longer scan and stay one launch per query
+    n, d, nq = 300007, 384, 200
+    res = {}
+    with sema.GpuIndex(d, n) as idx:
+        idx.append_synthetic(seed=1, row0=0, n=n, normalize=True)
+        Q = _unit(2, nq, d)
+        for k in (10, 50):
+            before = idx.launch_count
+            a = _stream_search(sema, idx, Q, k)
+            assert idx.launch_count - before == (1 if k == 10 else nq)
+            idx.set_scan_variant(902)              # one launch per query, chained
+            before = idx.launch_count
+            b = _stream_search(sema, idx, Q, k)
+            assert idx.launch_count - before == nq
+            idx.set_scan_variant(901)              # persistent whatever the size
+            before = idx.launch_count
+            c = _stream_search(sema, idx, Q, k)
+            assert idx.launch_count - before == 1
+            idx.set_scan_variant(900)
+            for x, y, z in zip(a, b, c):
+                assert np.array_equal(x, y) and np.array_equal(x, z)
+            res[k] = a
+        # persistent launches back to back on one handle: the control words are re-zeroed on the stream every time
+        idx.set_scan_variant(901)
+        for _ in range(3):
+            c = _stream_search(sema, idx, Q[:7], 10)
+            assert np.array_equal(c[0], res[10][0][:7]) and np.array_equal(c[1], res[10][1][:7])
+    assert np.array_equal(res[10][0], res[50][0][:, :10]) and np.array_equal(res[10][1], res[50][1][:, :10])
+
+
+def test_persistent_stream_with_nulls_tombstones_and_shard_exchange(sema, oracle_c):
+    n, d, k, nq = 20011, 384, 10, 13
+    X = _unit(1, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[::7] = 0
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as idx:
+        idx.set_row_base(1_000_000)
+        idx.append(X, valid=valid, normalize=False)
+        dead = np.arange(1, n, 11, dtype=np.uint64)
+        idx.tombstone(dead)
+        valid[dead] = 0
+        idx.set_scan_variant(901)
+        ids, sc, nf = _stream_search(sema, idx, Q, k)
+        g = sema.ShardGroup(idx, 1, 0)             # world = 1: the fused exchange runs against the rank's own buffer
+        try:
+            gids, gsc, gnf = _stream_search(sema, idx, Q, k, group=g)
+            gids2, gsc2, gnf2 = _stream_search(sema, idx, Q[:6], k, group=g)   # sequence numbers carry on
+            one_ids, _ = g.search(Q[3], k)         # host call after a persistent stream: still in step
+        finally:
+            g.close()
+        for i in range(nq):
+            r_ids, r_sc = oracle_c.scan(X, Q[i], k, 0, valid, id_base=1_000_000)
+            O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+        assert np.array_equal(ids, gids) and np.array_equal(sc, gsc) and np.array_equal(nf, gnf)
+        assert np.array_equal(ids[:6], gids2) and np.array_equal(sc[:6], gsc2)
+        assert np.array_equal(one_ids, ids[3, :nf[3]])
+
+
 @pytest.mark.parametrize("d,k", [(384, 10), (384, 50), (384, 128), (768, 100)])
 def test_host_query_path_equals_staged_path(sema, oracle_c, d, k):
     """sema_index_search: query by kernel parameter + results to mapped host memory (default) against
