@@ -299,7 +299,8 @@ def median_spread(xs):
 
 
 def k2_stream_bench(idx, Q, k, steps, warmup, repeats, dev, stream):
-    """Device-timed single-query stream on one GPU (inputs resident): -> (median ms/step, spread, ids, scores)."""
+    """Device-timed single-query stream on one GPU (inputs resident): -> (median ms/step, spread, ids, scores).
+    k2_stream_bench.launches = kernel launches of the last timed region (1 = the persistent stream kernel)."""
     import torch
     nq = len(Q)
     Qd = torch.from_numpy(Q).to(dev)
@@ -315,11 +316,13 @@ def k2_stream_bench(idx, Q, k, steps, warmup, repeats, dev, stream):
     ms = []
     for _ in range(repeats):
         torch.cuda.synchronize()
+        l0 = idx.launch_count
         e0.record(stream)
         idx.search_stream_device(Qs.data_ptr(), steps, k, ids_s.data_ptr(), sc_s.data_ptr(), nf_s.data_ptr())
         e1.record(stream)
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1) / steps)
+        k2_stream_bench.launches = idx.launch_count - l0
     idx.set_stream(None)
     med, spread = median_spread(ms)
     return med, spread, ids_s.cpu().numpy().astype(np.uint64), sc_s.cpu().numpy()
@@ -394,7 +397,9 @@ def sub_single_1m(a, hc, dev, stream):
         if hc is not None:
             fails = [f for f in (hc.check(i, a.k, ids[i], sc[i], prefix=rows) for i in range(min(N_ORACLE_QUERIES, len(Q)))) if f]
     rec = {"metric": metric_name(rows, a.dim, a.k), "value": 1e3 / ms, "unit": "queries/s", "ms_per_step": ms, "steps": steps,
-           "repeats": spread, "roofline": hbm_roofline(rows, a.dim, ms, "scan_topk_tma_kernel (K2)"),
+           "repeats": spread, "gpu_launches": int(k2_stream_bench.launches),
+           "roofline": hbm_roofline(rows, a.dim, ms, "scan_stream_kernel (K2, one persistent launch for the stream of %d queries)" % steps
+                                    if k2_stream_bench.launches < steps else "scan_topk_tma_kernel (K2, one chained launch per query)"),
            "e2e": {"value": 1e3 / e2e_ms, "unit": "queries/s", "ms_per_step": e2e_ms, "latency": lat,
                    "h2d_bytes_per_step": a.dim * 4, "d2h_bytes_per_step": 8 + 12 * a.k},
            "oracle_checked_queries": 0 if hc is None else min(N_ORACLE_QUERIES, len(Q)), "oracle_failures": fails,
@@ -932,12 +937,23 @@ def run_ours(a):
         persistent = bool(use_stream and launches < a.steps)
         kern = ("scan_stream_kernel (K2, TMA ring, one persistent launch per query stream)" if persistent
                 else "scan_topk_tma_kernel (K2, TMA ring)" if (a.variant <= 0 and a.dim in (384, 768)) else "scan_topk_kernel (K2, register-fed)")
+        tsrc = "profiles/r01_k2_scan_full_raw.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch = one pass over the corpus)"
+        if persistent:
+            try:   # the persistent launch's own capture: DRAM bytes of the launch divided by its passes
+                t2 = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+                per_pass = t2.get(f"k2_stream_{a.rows}x{a.dim}_per_pass") if (world == 1 and a.k == 10) else None
+                traffic = per_pass * a.steps if per_pass else None
+                tsrc = (f"profiles/r02_k2_stream_full_raw.csv: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of "
+                        f"{t2.get('k2_stream_capture_passes')} passes, per pass ({per_pass} B), times this launch's {a.steps} passes")
+            except Exception:
+                traffic = None
         roof = hbm_roofline(shard_rows, a.dim, dev_ms, kern, traffic)
-        roof["traffic_source"] = "profiles/r01_k2_scan_full_raw.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum; per pass over the corpus)" if traffic else None
+        roof["traffic_source"] = tsrc if traffic else None
         tail = "" if world == 1 else ", which includes the top-k exchange and the global merge"
         if persistent:
             roof["passes_per_launch"] = a.steps
-            roof["algorithmic_bytes_per_launch"] = int(shard_rows) * a.dim * 4 * a.steps
+            roof["algorithmic_bytes"] = int(shard_rows) * a.dim * 4 * a.steps      # per launch, like traffic
+            roof["algorithmic_bytes_per_pass"] = int(shard_rows) * a.dim * 4
             roof["note"] = (f"ONE K2 launch scans the corpus once per step ({a.steps} passes per launch): achieved = "
                             "passes * rows_per_gpu*dim*4 bytes / launch duration = rows_per_gpu*dim*4 / device time per step" + tail)
         else:

@@ -174,13 +174,19 @@ int sema_index_search_batch(sema_index *idx, const float *Q, uint32_t nq, uint32
  * stage may still be running on the query stream; results are ordered after it on that stream. */
 int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
-/* A query stream: nq independent single-query searches (kernel K2 once per query, one HBM pass
- * each — the reference's own pattern of one nearest_to() call per query, lance_indexer.rs:121-126)
- * issued back to back on the query stream.  With dim 384 / 768 and k <= 128 consecutive launches
- * are chained with programmatic dependent launch: query i+1 starts scanning on the SMs query i has
- * left while i's last block still merges, so the stream runs at the HBM rate without a per-query
- * launch / merge gap.  Same layouts and results as sema_index_search_batch_device; all rows the
- * stream sees are one snapshot. */
+/* A query stream: nq independent single-query searches (kernel K2, one HBM pass per query — the
+ * reference's own pattern of one nearest_to() call per query, lance_indexer.rs:121-126) issued back
+ * to back on the query stream.  With dim 384 / 768 and k <= 128 the stream runs at the HBM rate
+ * without a per-query launch / merge gap, in one of two forms the library picks by corpus size:
+ * ONE persistent (cooperative) launch for the whole stream — a TMA producer warp keeps streaming
+ * rows across query boundaries while a finisher warp merges, exchanges (shard groups) and publishes
+ * the query just scanned — when one scan is long against that finisher's work (k <= 16: about 100 k
+ * rows of dim 384 and up; larger k: about 800 k rows), otherwise one launch per query with
+ * consecutive launches chained by programmatic dependent launch (query i+1 starts scanning on the
+ * SMs query i has left while i's last block still merges).  Both forms give bit-identical results.
+ * If the device cannot hold the persistent grid at once (SM partitioning), the launch is refused by
+ * the driver and the stream falls back to the chained form.  Same layouts and results as
+ * sema_index_search_batch_device; all rows the stream sees are one snapshot. */
 int sema_index_search_stream_device(sema_index *idx, const float *Q_dev, uint32_t nq, uint32_t k,
                                     uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
 /* mode 0 = automatic: when the shape allows and nq >= 4, a precision cascade on the tensor cores —
@@ -271,9 +277,11 @@ int sema_shard_group_search_collect(sema_shard_group *g, uint64_t ticket, uint64
                                     uint32_t *n_found);
 int sema_shard_group_search_device(sema_shard_group *g, const float *q_dev, uint32_t k,
                                    uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
-/* nq group searches issued back to back (Q_dev: nq x dim, results nq x k); consecutive launches
- * are chained like sema_index_search_stream_device, so a rank's next scan also overlaps the wait
- * for its peers' keys. */
+/* nq group searches issued back to back (Q_dev: nq x dim, results nq x k), in the two forms of
+ * sema_index_search_stream_device: one persistent launch per rank whose finisher warp runs the peer
+ * exchange of query i while the rest of the GPU scans query i+1, or launches chained with programmatic
+ * dependent launch — either way a rank's next scan overlaps the wait for its peers' keys.  Ranks may
+ * mix the two forms (both use the same sequence numbers), results are identical. */
 int sema_shard_group_search_stream_device(sema_shard_group *g, const float *Q_dev, uint32_t nq, uint32_t k,
                                           uint64_t *ids_dev, float *scores_dev, uint32_t *n_found_dev);
 int sema_shard_group_destroy(sema_shard_group *g);
@@ -312,7 +320,9 @@ int sema_index_read_rows(sema_index *idx, uint64_t first_row, uint64_t n, float 
  * 500 / 501 = host searches staged through H2D + D2H copies / query by kernel parameter + results to mapped
  * host memory (default); 600 / 601 = query streams unchained / chained (default); 700 / 701 = K3 single-pass
  * stage on the single-CTA kernel (default) / on CTA pairs (tcgen05 cta_group::2); 800 + d = K3 producer
- * prefetches into L2 d stages ahead (default 0: measured no gain); 1100 / 1101 = a K3 stage as one launch / as
+ * prefetches into L2 d stages ahead (default 0: measured no gain); 900 / 901 / 902 = query streams as one
+ * persistent launch when a scan is long enough (default) / whenever the shape allows / never (always one launch
+ * per query); 1100 / 1101 = a K3 stage as one launch / as
  * two concurrent launches, clusters of 4 plus clusters of 2 on the SMs those leave free (default); 1200 + w = row
  * weight of a 4-cluster partition in that split, 0.70 + w / 100 (0 = built-in 1.05); negative = query.
  * Returns the value set, or -1 for a value this build does not have. */

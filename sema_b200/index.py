@@ -214,8 +214,9 @@ class GpuIndex:
 
     def search_stream_device(self, q_ptr: int, nq: int, k: int, ids_ptr: int, scores_ptr: int,
                              nfound_ptr: int) -> None:
-        """A stream of nq independent single-query scans (K2 each, consecutive launches chained with
-        programmatic dependent launch); device pointers, results nq x k, nothing synchronises."""
+        """A stream of nq independent single-query scans (K2: one persistent launch for the whole stream when a
+        scan is long enough, else one launch per query chained with programmatic dependent launch; identical
+        results); device pointers, results nq x k, nothing synchronises."""
         check(self._L.sema_index_search_stream_device(self._h, C.c_void_p(q_ptr), nq, k, C.c_void_p(ids_ptr),
                                                       C.c_void_p(scores_ptr), C.c_void_p(nfound_ptr)))
 
