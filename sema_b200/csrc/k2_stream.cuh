@@ -293,6 +293,7 @@ scan_stream_kernel(const __grid_constant__ StreamParams p)
                     }
                 }
                 dead = __shfl_sync(FULL, bad, 0) != 0;
+                __syncwarp();                                      // lane 0's acquire orders every lane's stores below
                 if (dead) {
                     if (lane == 0) p.res_nfound[q] = 0xffffffffu;
                     continue;
