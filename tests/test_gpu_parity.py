@@ -1280,6 +1280,65 @@ def test_persistent_stream_with_nulls_tombstones_and_shard_exchange(sema, oracle
         assert np.array_equal(one_ids, ids[3, :nf[3]])
 
 
+def test_two_persistent_streams_on_one_device_at_once(sema):
+    """Two handles on one GPU, each running a persistent (cooperative, one CTA per SM) stream launch on its own CUDA
+    stream with nothing synchronising in between: the two grids cannot be co-resident, so the launches must be
+    serialised by the device rather than interleaved into a deadlock; both must give the single-call results."""
+    import torch
+    dev = torch.device("cuda:0")
+    n, d, k, nq = 120001, 384, 10, 60
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n) as a, sema.GpuIndex(d, n) as b:
+        a.append_synthetic(seed=1, row0=0, n=n, normalize=True)
+        b.append_synthetic(seed=7, row0=0, n=n, normalize=True)
+        ref = [[h.search(q, k) for q in Q] for h in (a, b)]
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        Qd = torch.from_numpy(np.ascontiguousarray(Q)).to(dev)
+        out = [(torch.zeros((nq, k), dtype=torch.int64, device=dev), torch.zeros((nq, k), dtype=torch.float32, device=dev),
+                torch.zeros(nq, dtype=torch.int32, device=dev)) for _ in range(2)]
+        torch.cuda.synchronize()
+        a.set_scan_variant(901)
+        b.set_scan_variant(901)
+        a.set_stream(s1.cuda_stream)
+        b.set_stream(s2.cuda_stream)
+        try:
+            for _ in range(3):          # A, B, A, B, ... queued without a synchronise
+                for h, (ids, sc, nf) in zip((a, b), out):
+                    h.search_stream_device(Qd.data_ptr(), nq, k, ids.data_ptr(), sc.data_ptr(), nf.data_ptr())
+            torch.cuda.synchronize()
+        finally:
+            a.set_stream(None)
+            b.set_stream(None)
+        for r, (ids, sc, nf) in zip(ref, out):
+            ids, sc, nf = ids.cpu().numpy().astype(np.uint64), sc.cpu().numpy(), nf.cpu().numpy()
+            for i in range(nq):
+                assert nf[i] == k and np.array_equal(ids[i], r[i][0]) and np.array_equal(sc[i], r[i][1])
+
+
+def test_persistent_stream_while_rows_are_being_appended(sema, oracle_c):
+    """config 5's interleave with the persistent kernel: the stream scans the snapshot it started with while K1 keeps
+    appending on the ingest stream (its blocks compete for SMs with the cooperative grid)."""
+    d, k, nq, n0, batch, nb = 384, 10, 40, 110000, 20000, 6
+    X = _unit(1, n0 + batch * nb, d)
+    Q = _unit(2, nq, d)
+    with sema.GpuIndex(d, n0 + batch * nb) as idx:
+        idx.append(X[:n0], normalize=False)
+        idx.set_scan_variant(901)
+        for b in range(nb):
+            lo = n0 + b * batch
+            idx.append(X[lo:lo + batch], normalize=False, asynchronous=True)
+            ids, sc, nf = _stream_search(sema, idx, Q, k)
+            snap = idx.last_snapshot
+            assert n0 <= snap <= lo + batch and (snap - n0) % batch == 0
+            for i in (0, nq // 2, nq - 1):
+                r_ids, r_sc = oracle_c.scan(X[:snap], Q[i], k)
+                O.check_parity(ids[i, :nf[i]], sc[i, :nf[i]], r_ids, r_sc)
+        idx.flush()
+        ids, sc, nf = _stream_search(sema, idx, Q, k)
+        r_ids, r_sc = oracle_c.scan(X, Q[5], k)
+        O.check_parity(ids[5, :nf[5]], sc[5, :nf[5]], r_ids, r_sc)
+
+
 @pytest.mark.parametrize("d,k", [(384, 10), (384, 50), (384, 128), (768, 100)])
 def test_host_query_path_equals_staged_path(sema, oracle_c, d, k):
     """sema_index_search: query by kernel parameter + results to mapped host memory (default) against
