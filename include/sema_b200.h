@@ -181,7 +181,7 @@ int sema_index_search_batch_device(sema_index *idx, const float *Q_dev, uint32_t
  * ONE persistent (cooperative) launch for the whole stream — a TMA producer warp keeps streaming
  * rows across query boundaries while a finisher warp merges, exchanges (shard groups) and publishes
  * the query just scanned — when one scan is long against that finisher's work (k <= 16: about 100 k
- * rows of dim 384 and up; larger k: about 800 k rows), otherwise one launch per query with
+ * rows of dim 384 and up; k <= 64: about 600 k rows; larger k: about 800 k rows), otherwise one launch per query with
  * consecutive launches chained by programmatic dependent launch (query i+1 starts scanning on the
  * SMs query i has left while i's last block still merges).  Both forms give bit-identical results.
  * If the device cannot hold the persistent grid at once (SM partitioning), the launch is refused by

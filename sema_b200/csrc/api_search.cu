@@ -314,8 +314,9 @@ int scan_query(sema_index *s, const float *q_dev, uint32_t n, uint32_t k, uint64
 }
 
 // One persistent launch for the whole stream?  Shapes of the TMA kernel only; by default only when one scan is long
-// against the finisher warp's per-query work (block merge + the last block's merge over all blocks: a few us for
-// k <= 16, tens of us for k = 100), so short scans keep the chained launches that finish a query on eight warps.
+// against the finisher warp's per-query work (block merge + the last block's merge over all blocks, one warp: ~19 us
+// per query for k <= 16, 50 - 100 us for larger k), so short scans keep the chained launches that finish a query on
+// eight warps.
 bool stream_kernel_ok(const sema_index *s, uint32_t nq, uint32_t n, uint32_t k)
 {
     const uint32_t ld4 = s->ld / 4;
@@ -323,7 +324,10 @@ bool stream_kernel_ok(const sema_index *s, uint32_t nq, uint32_t n, uint32_t k)
     if (s->ld != s->dim || (ld4 != 96 && ld4 != 192)) return false;
     if (s->stream_mode == 1) return true;
     const uint64_t floats = (uint64_t)n * s->ld;
-    return floats >= (k <= 16 ? 38000000ull : 300000000ull);    // ~20 us / ~160 us of scan at 7.4 TB/s (measured: 100 k x 384 rows at k = 10 gain 8 %)
+    // measured crossovers (scripts/gpu_r2_stream_thr.sh, dim 384): the finisher chain costs ~19 us per query for k <= 16
+    // (persistent wins from 100 k rows: 22.9 against 24.9 us), ~50 - 100 us for the bitonic merges of k = 17 .. 64
+    // (loses at 300 k rows, wins at 600 k: 122 against 126 us) and more for k = 65 .. 128 (600 k rows: +1 %, 1 M: +1 - 5 %)
+    return floats >= (k <= 16 ? 38000000ull : k <= 64 ? 230000000ull : 300000000ull);
 }
 
 int stream_kernel_launch(sema_index *s, const float *Q, uint32_t nq, uint32_t n, uint32_t k, uint64_t *ids_d, float *sc_d,
