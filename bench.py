@@ -58,10 +58,13 @@ def parse():
     ap.add_argument("--variant", type=int, default=-1, help="K2 kernel variant (tuning)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: fused = P2P stores + merge inside K2's last block; nccl = all-gather + K4")
-    ap.add_argument("--workload", default="single", choices=["single", "batch", "ingest", "config1", "pool"],
+    ap.add_argument("--workload", default="single", choices=["single", "batch", "ingest", "config1", "pool", "maintenance"],
                     help="single = headline single-query scan (K2) + the sub-configs; batch = BASELINE configs[2], nq-query "
                          "batches (K3); ingest = configs[4], streaming ingest (K1) interleaved with queries; "
-                         "config1 = ~10k-chunk synthetic markdown corpus through the StorageManager boundary; pool = K0")
+                         "config1 = ~10k-chunk synthetic markdown corpus through the StorageManager boundary; pool = K0; "
+                         "maintenance = SURVEY 8(f) rows 1-2: tombstones, compaction, disk cache save / load")
+    ap.add_argument("--maint-rows", type=int, default=4_000_000, help="rows of the --workload maintenance index")
+    ap.add_argument("--maint-save-rows", type=int, default=1_000_000, help="rows of the index saved to / loaded from disk")
     ap.add_argument("--ingest-batch", type=int, default=65536, help="rows per appended batch (--workload ingest)")
     ap.add_argument("--nq", type=int, default=1024, help="queries per batch (--workload batch)")
     ap.add_argument("--batch-mode", type=int, default=2, help="0 auto (cascade), 1 K2 per query, 2 K3 three-pass split, 3 K3 single pass")
@@ -1306,6 +1309,121 @@ def run_pool(a):
     print(json.dumps(line), flush=True)
 
 
+def run_maintenance(a):
+    """SURVEY.md 8(f) rows 1-2 measured: remove_file_chunks' device side (tombstones: src/storage/lance_indexer.rs:234-250),
+    compaction, and the on-disk vector cache.  Every phase is followed by oracle checks of searches on the result."""
+    import tempfile
+
+    import torch
+
+    import sema_b200
+    need_gpu()
+    torch.cuda.set_device(0)
+    rows, dim, k = a.maint_rows, a.dim, a.k
+    hc = HostCorpus(rows, dim, 16)
+    rng = np.random.default_rng(5)
+    peaks, _ = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rec = {}
+    file_rows = np.arange(rows // 3, rows // 3 + 50, dtype=np.uint64)
+    scattered = np.sort(rng.choice(rows, rows // 10, replace=False)).astype(np.uint64)
+    with sema_b200.GpuIndex(dim, rows, device=0) as idx:
+
+        def check(valid, X, tag):
+            from oracle import oracle as O
+            fails = []
+            for qi in range(4):
+                ids, sc = idx.search(hc.Q[qi], k)
+                r_ids, r_sc = hc.c.scan(X, hc.Q[qi], k, 0, valid)      # the oracle over its own rows and validity bytes
+                try:
+                    O.check_parity(ids, sc, r_ids, r_sc)
+                except AssertionError as e:
+                    fails.append(f"{tag} query {qi}: {e}")
+            return fails
+
+        fails = []
+        map_buf = np.full(rows, 7, dtype=np.uint64)
+        ROUNDS = 3                         # the index is rebuilt and the same rows removed each round; phases report the median
+        t_tomb = {"one_file_50_chunks": [], "10pct_of_rows": []}
+        t_compact = []
+        l0 = idx.launch_count
+        for rnd in range(ROUNDS):
+            if rnd:
+                idx.compact_keep(np.zeros(len(idx), np.uint8))           # empty the index (every row dropped), refill
+            idx.append_synthetic(seed=1, row0=0, n=rows, normalize=True)
+            valid = np.ones(rows, np.uint8)
+            # (1) a "file" of 50 consecutive chunks removed (the reference deletes by file_path), then 10 % of all rows
+            for name, dead in (("one_file_50_chunks", file_rows), ("10pct_of_rows", scattered)):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                idx.tombstone(dead)
+                t_tomb[name].append(time.perf_counter() - t0)
+                valid[dead.astype(np.int64)] = 0
+                if rnd == 0:
+                    fails += check(valid, hc.X, "after tombstone " + name)
+            # (2) compaction: plan on the device (prefix sums over the keep flags), ordered gather of the surviving rows
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            new_of_old = idx.compact(out=map_buf)        # the caller's own, already-touched buffer (as a Rust Vec would be)
+            t_compact.append(time.perf_counter() - t0)
+        for name, dead in (("one_file_50_chunks", file_rows), ("10pct_of_rows", scattered)):
+            dt = float(np.median(t_tomb[name]))
+            rec["tombstone_" + name] = {"rows": int(len(dead)), "seconds": dt, "rows_per_s": len(dead) / dt, "all_seconds": t_tomb[name],
+                                        "note": "synchronous call: H2D of the row ids, NaN-poison rows (+ K3 planes when built), validity bytes"}
+        dt = float(np.median(t_compact))
+        live = int(valid.sum())
+        moved = live - int(np.argmin(valid))                      # rows behind the first dropped row all move
+        assert len(idx) == live
+        keep = valid.astype(bool)
+        Xc = hc.X[keep]
+        ok_map = bool(np.array_equal(new_of_old[keep], np.arange(live, dtype=np.uint64)) and np.all(new_of_old[~keep] == np.uint64(2**64 - 1)))
+        rec["compact"] = {"rows_before": rows, "rows_after": live, "rows_moved": moved, "seconds": dt, "all_seconds": t_compact,
+                          "algorithmic_bytes": 2 * moved * dim * 4,
+                          "roofline": {"bound": "hbm", "achieved": 2 * moved * dim * 4 / dt / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": 2 * moved * dim * 4 / dt / 1e9 / peak, "traffic": None,
+                                       "note": "whole synchronous call — scratch allocation, plan kernels (prefix sums over the keep flags), "
+                                               f"the {rows * 8 / 1e6:.0f} MB old->new map copied to pageable host memory (what the caller's chunk table "
+                                               "needs; the largest phase of the call), gather kernels — against 1 read + 1 write of every moved row"},
+                          "old_to_new_map_correct": ok_map}
+        fails += check(None, Xc, "after compaction")
+        fails += [] if ok_map else ["compaction: old -> new row map is wrong"]
+        launches = (idx.launch_count - l0) // ROUNDS
+    # (3) disk cache: save / load round trip of a smaller index (page-cache speed on this box, stated as such)
+    srows = min(a.maint_save_rows, rows)
+    with tempfile.TemporaryDirectory() as td, sema_b200.GpuIndex(dim, srows, device=0) as idx:
+        idx.append_synthetic(seed=1, row0=0, n=srows, normalize=True)
+        path = os.path.join(td, "vectors.semaidx")
+        t0 = time.perf_counter()
+        idx.save(path)
+        ts = time.perf_counter() - t0
+        size = os.path.getsize(path)
+        t0 = time.perf_counter()
+        idx2 = sema_b200.GpuIndex.load(path, device=0)
+        tl = time.perf_counter() - t0
+        try:
+            same = True
+            for qi in range(4):
+                a1, b1 = idx.search(hc.Q[qi], k)
+                a2, b2 = idx2.search(hc.Q[qi], k)
+                same &= bool(np.array_equal(a1, a2) and np.array_equal(b1, b2))
+                f = hc.check(qi, k, a2, b2, prefix=srows)
+                fails += [f] if f else []
+        finally:
+            idx2.close()
+        rec["disk_cache"] = {"rows": srows, "file_bytes": size, "save_seconds": ts, "save_GBps": size / ts / 1e9,
+                             "load_seconds": tl, "load_GBps": size / tl / 1e9, "loaded_index_answers_bit_identically": same,
+                             "note": "D2H + write / read + H2D through a temporary directory (page cache, not a disk benchmark)"}
+        fails += [] if same else ["disk cache: loaded index answers differently"]
+    line = {"metric": f"compaction_rows_per_s_{rows}x{dim}_fp32_10pct_dropped", "value": rec["compact"]["rows_moved"] / rec["compact"]["seconds"],
+            "unit": "rows/s", "n_gpus": 1, "steps": 1, "warmup": 0, "ms_per_step": rec["compact"]["seconds"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{rows}x{dim} fp32 index: tombstone one file's 50 chunks, tombstone 10 % of the rows, compact, "
+                                   f"then save / load a {srows}-row index (SURVEY.md 8(f) rows 1-2)", "k": k},
+            "roofline": rec["compact"]["roofline"], "phases": rec, "gpu_launches": int(launches),
+            "oracle_checked_queries": 4 * 4 + 4, "oracle_failures": fails, "verified": not fails}
+    print(json.dumps(line), flush=True)
+
+
 def run_ingest(a):
     """BASELINE.json configs[4] alone (see ingest_measure)."""
     import torch
@@ -1415,6 +1533,8 @@ def main():
         run_config1(a)
     elif a.workload == "pool":
         run_pool(a)
+    elif a.workload == "maintenance":
+        run_maintenance(a)
     else:
         run_ours(a)
 

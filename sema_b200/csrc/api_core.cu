@@ -265,6 +265,8 @@ int sema_index_destroy(sema_index *s)
         s->X = nullptr; s->valid = nullptr; s->planes = nullptr;
     }
     cudaFree(s->X); cudaFree(s->valid); cudaFree(s->q_dev); cudaFreeHost(s->q_pin);
+    cudaFree(s->cs.flags); cudaFree(s->cs.new_valid); cudaFree(s->cs.src); cudaFree(s->cs.tiles); cudaFree(s->cs.map);
+    cudaFree(s->cs.head); cudaFree(s->cs.tmp);
     cudaFree(s->partials); cudaFree(s->ticket); cudaFree(s->stream_ctl); cudaFree(s->keys_dev); cudaFree(s->res_dev);
     cudaFreeHost(s->res_pin); cudaFreeHost(s->res_map); cudaFree(s->Q_dev); cudaFree(s->bids_dev); cudaFree(s->bsc_dev);
     cudaFree(s->bnf_dev); cudaFree(s->tomb_dev);
@@ -427,67 +429,114 @@ int sema_index_compact_keep(sema_index *s, const uint8_t *keep, uint64_t *new_ro
     if (s->poisoned) return fail(SEMA_ERR_CUDA, "index unusable: an earlier compaction failed half-way");
     CK(cudaStreamSynchronize(s->stream));
     const uint64_t n = s->n_rows;
-    std::vector<uint8_t> valid, new_valid;
-    std::vector<uint32_t> src;   // src[new] = old, ascending
-    try {
-        valid.resize(n ? n : 1);
-        src.reserve(n);
-        new_valid.reserve(n);
-    } catch (const std::exception &) {
-        return fail(SEMA_ERR_NOMEM, "host allocation failed (%llu rows)", (unsigned long long)n);
+    if (n == 0) {
+        if (n_live_out) *n_live_out = 0;
+        return SEMA_OK;
     }
-    if (n) CK(cudaMemcpy(valid.data(), s->valid, n, cudaMemcpyDeviceToHost));
-    for (uint64_t r = 0; r < n; ++r) {
-        if (keep ? keep[r] != 0 : valid[r] != 0) {
-            new_valid.push_back(valid[r]);
-            if (new_row_of_old) new_row_of_old[r] = src.size();
-            src.push_back((uint32_t)r);
-        } else if (new_row_of_old) {
-            new_row_of_old[r] = ~0ull;
-        }
+    // SEMA_TRACE=1: phase times of this call on stderr (host clock; every phase below ends synchronised or is host work)
+    static const bool trace = getenv("SEMA_TRACE") != nullptr;
+    timespec t_prev;
+    clock_gettime(CLOCK_MONOTONIC, &t_prev);
+    auto phase = [&](const char *name) {
+        if (!trace) return;
+        timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[sema compact] %-28s %9.3f ms\n", name, (t.tv_sec - t_prev.tv_sec) * 1e3 + (t.tv_nsec - t_prev.tv_nsec) * 1e-6);
+        t_prev = t;
+    };
+    // ---- plan on the device (k1_ingest.cuh): which rows stay (the caller's keep flags, else the validity bytes),
+    // their new positions by prefix sums, the ascending gather list src[new] = old, the compacted validity bytes and
+    // the old -> new map the caller's chunk table needs.  Nothing has moved yet: a failure here is an ordinary error.
+    const uint32_t tiles = (uint32_t)((n + COMPACT_TILE - 1) / COMPACT_TILE);
+    const uint64_t C = 1u << 16;                         // rows per gather chunk
+    sema_index::CompactScratch &d = s->cs;      // grown on demand, kept between calls, freed with the handle
+    uint32_t *tile_count = nullptr, *tile_off = nullptr;
+    {
+        auto grow = [&](auto **p, size_t *cap, size_t bytes) { return ensure(reinterpret_cast<void **>(p), cap, bytes ? bytes : 1); };
+        int arc = SEMA_OK;
+        if (keep) arc = grow(&d.flags, &d.flags_cap, n);
+        if (!arc) arc = grow(&d.new_valid, &d.new_valid_cap, n);
+        if (!arc) arc = grow(&d.src, &d.src_cap, n * sizeof(uint32_t));
+        if (!arc) arc = grow(&d.tiles, &d.tiles_cap, 2 * (size_t)tiles * sizeof(uint32_t));
+        if (!arc) arc = grow(&d.head, &d.head_cap, 2 * sizeof(unsigned long long));
+        if (!arc && new_row_of_old) arc = grow(&d.map, &d.map_cap, n * sizeof(unsigned long long));
+        if (arc) return arc;                     // ensure() has set the error text; nothing has moved
+        tile_count = d.tiles;
+        tile_off = d.tiles + tiles;
     }
-    const uint64_t live = src.size();
+    cudaError_t e = cudaSuccess;
+    phase("scratch allocation");
+    const uint8_t *flags = s->valid;
+    if (keep) {
+        CK(cudaMemcpyAsync(d.flags, keep, n, cudaMemcpyHostToDevice, s->stream));
+        flags = d.flags;
+    }
+    unsigned long long head[2] = {0ull, (unsigned long long)n};
+    CK(cudaMemcpyAsync(d.head, head, sizeof head, cudaMemcpyHostToDevice, s->stream));
+    compact_count_kernel<<<tiles, INGEST_THREADS, 0, s->stream>>>(flags, n, tile_count, d.head + 1);
+    compact_scan_tiles_kernel<<<1, INGEST_THREADS, 0, s->stream>>>(tile_count, tiles, tile_off, d.head);
+    compact_emit_kernel<<<tiles, INGEST_THREADS, 0, s->stream>>>(flags, s->valid, n, tile_off, d.src, d.new_valid,
+                                                                 new_row_of_old ? d.map : nullptr);
+    CK(cudaGetLastError());
+    s->launches += 3;
+    CK(cudaMemcpyAsync(head, d.head, sizeof head, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    const uint64_t live = head[0], first_moved = head[1] < live ? head[1] : live;   // rows before the first dropped row stay put
+    phase("plan kernels");
+    if (new_row_of_old) CK(cudaMemcpy(new_row_of_old, d.map, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    phase("old->new map to the host");
     if (n_live_out) *n_live_out = live;
     if (live == n) return SEMA_OK;  // nothing to drop
-    // gather through a bounce buffer, chunk by chunk in ascending order: a chunk's destination
-    // [j*C, (j+1)*C) never overlaps a later chunk's sources (src[i] >= i)
-    const uint64_t C = 1u << 16;
-    float *tmp = nullptr;
-    uint32_t *src_dev = nullptr;
-    cudaError_t e = cudaMalloc(&tmp, C * s->ld * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&src_dev, C * sizeof(uint32_t));
-    if (e != cudaSuccess) {
-        cudaFree(tmp); cudaFree(src_dev); cudaGetLastError();
-        return fail(SEMA_ERR_NOMEM, "compaction scratch: %s", cudaGetErrorString(e));   // nothing has moved yet
+    // first source row of every gather chunk (one strided copy): decides bounce / direct below
+    const uint64_t n_chunks = (live - first_moved + C - 1) / C;
+    std::vector<uint32_t> chunk_src;
+    try {
+        chunk_src.resize(n_chunks ? n_chunks : 1);
+    } catch (const std::exception &) {
+        return fail(SEMA_ERR_NOMEM, "host allocation failed");
     }
-    uint64_t first_moved = 0;
-    while (first_moved < live && src[first_moved] == first_moved) ++first_moved;   // untouched prefix
+    if (n_chunks)
+        CK(cudaMemcpy2D(chunk_src.data(), sizeof(uint32_t), d.src + first_moved, C * sizeof(uint32_t), sizeof(uint32_t), n_chunks,
+                        cudaMemcpyDeviceToHost));
+    bool any_bounce = false;
+    for (uint64_t ci = 0, at = first_moved; ci < n_chunks; ++ci, at += C)
+        any_bounce = any_bounce || chunk_src[ci] < at + ((live - at) < C ? (live - at) : C);
+    if (any_bounce) {       // the bounce buffer (one chunk of rows) only when some chunk's sources overlap its destination
+        const int arc = ensure(reinterpret_cast<void **>(&d.tmp), &d.tmp_cap, C * s->ld * sizeof(float));
+        if (arc) return arc;                         // nothing has moved yet
+    }
+    phase("chunk heads to the host");
+    // ---- ordered gather, chunk by chunk in ascending order, everything queued on the query stream with ONE
+    // synchronise at the end.  src[i] >= i, so a chunk's destination [at, at + m) never overlaps a LATER chunk's
+    // sources.  It may overlap its OWN sources while fewer than m rows have been dropped before it: such a chunk goes
+    // through a bounce buffer (gather, then copy into place: 2 reads + 2 writes per row).  As soon as
+    // src[at] >= at + m — from the first 65 536 dropped rows on — chunks are gathered straight into place (1 read +
+    // 1 write per row).
     // From the first chunk on, rows move in place: an error half-way would leave X out of step with the
     // validity bytes, the row count and the caller's chunk table.  It is reported, the scratch
     // buffers are released, and the handle refuses further work instead of answering from mixed rows.
-    const char *what = nullptr;
-    for (uint64_t at = first_moved; at < live && e == cudaSuccess; at += C) {
+    const char *what = "gather kernel";
+    uint64_t ci = 0;
+    for (uint64_t at = first_moved; at < live && e == cudaSuccess; at += C, ++ci) {
         const uint64_t m = (live - at) < C ? (live - at) : C;
-        what = "copying the gather list";
-        e = cudaMemcpyAsync(src_dev, src.data() + at, m * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream);
-        if (e != cudaSuccess) break;
+        const bool direct = chunk_src[ci] >= at + m;       // every source of this chunk lies beyond its destination
         uint64_t blocks = (m * 32 + INGEST_THREADS - 1) / INGEST_THREADS;
         if (blocks > (uint64_t)s->num_sms * 16) blocks = (uint64_t)s->num_sms * 16;
-        gather_rows_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, src_dev, m, tmp);
+        gather_rows_kernel<<<(unsigned)blocks, INGEST_THREADS, 0, s->stream>>>(s->X, s->ld, d.src + at, m, direct ? s->X + at * s->ld : d.tmp);
         what = "gather kernel";
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         s->launches++;
-        what = "moving a chunk into place";
-        e = cudaMemcpyAsync(s->X + at * s->ld, tmp, m * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);   // src_dev / tmp are reused by the next chunk
+        if (!direct) {
+            what = "moving a chunk into place";          // stream order keeps tmp safe: the next gather runs after this copy
+            e = cudaMemcpyAsync(s->X + at * s->ld, d.tmp, m * s->ld * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
+        }
     }
     if (e == cudaSuccess && live) {
         what = "writing the validity bytes";
-        e = cudaMemcpyAsync(s->valid, new_valid.data(), live, cudaMemcpyHostToDevice, s->stream);
+        e = cudaMemcpyAsync(s->valid, d.new_valid, live, cudaMemcpyDeviceToDevice, s->stream);
     }
     if (e == cudaSuccess) { what = "final synchronise"; e = cudaStreamSynchronize(s->stream); }
-    cudaFree(tmp);
-    cudaFree(src_dev);
+    phase("gather + validity bytes");
     if (e != cudaSuccess) {
         cudaGetLastError();
         s->poisoned = true;

@@ -119,6 +119,16 @@ struct sema_index {
     size_t batch_cap_q = 0, batch_cap_res = 0, batch_cap_nf = 0;
     uint64_t *tomb_dev = nullptr;
     size_t tomb_cap = 0;
+    // compaction scratch, kept between calls (cudaMalloc / cudaFree cost 1 - 20 ms per call on the bench boxes, more
+    // than the compaction itself): keep flags, compacted validity bytes, gather list, tile counts + offsets,
+    // old -> new map, [live rows, first dropped row], bounce buffer of one gather chunk
+    struct CompactScratch {
+        uint8_t *flags = nullptr, *new_valid = nullptr;
+        uint32_t *src = nullptr, *tiles = nullptr;
+        unsigned long long *map = nullptr, *head = nullptr;
+        float *tmp = nullptr;
+        size_t flags_cap = 0, new_valid_cap = 0, src_cap = 0, tiles_cap = 0, map_cap = 0, head_cap = 0, tmp_cap = 0;
+    } cs;
     std::deque<sema_impl::Pending> pending;
     int variant = 0;
     uint64_t launches = 0;

@@ -198,4 +198,116 @@ gather_rows_kernel(const float *X, uint32_t ld, const uint32_t *src, uint64_t m,
     }
 }
 
+// ---- compaction plan on the device: flags -> prefix sums -> gather list, old->new map, compacted validity bytes ----
+// Three kernels over tiles of COMPACT_TILE rows (256 threads x 16 flags): per-tile live counts, one block scanning
+// the tile counts, and an emit pass that re-derives each thread's offset inside its tile.  Replaces a host loop over
+// every row (the reference deletes by predicate and lets LanceDB rewrite fragments: src/storage/lance_indexer.rs:234-250).
+constexpr int COMPACT_TILE = 4096;
+
+__device__ __forceinline__ uint32_t compact_load16(const uint8_t *flags, uint64_t base, uint64_t n, uint8_t (&f)[16])
+{
+    uint32_t c = 0;
+    if (base + 16 <= n) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(flags + base);    // base is a multiple of 16, flags 256-byte aligned
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { f[i] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8)); c += f[i] != 0; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { f[i] = (base + i < n) ? flags[base + i] : 0; c += f[i] != 0; }
+    }
+    return c;
+}
+
+// inclusive scan of one value per thread over a block of 256 threads (8 warps); returns the inclusive sum, *total = block sum
+__device__ __forceinline__ uint32_t compact_block_scan(uint32_t v, uint32_t *warp_sums, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < INGEST_THREADS / 32; ++w) {
+        const uint32_t ws = warp_sums[w];
+        if (w < warp) before += ws;
+        all += ws;
+    }
+    __syncthreads();
+    *total = all;
+    return x + before;
+}
+
+// tile_count[b] = flags set in tile b; *first_dropped = lowest row whose flag is clear (n if none; initialised by the host)
+__global__ void __launch_bounds__(INGEST_THREADS)
+compact_count_kernel(const uint8_t *flags, uint64_t n, uint32_t *tile_count, unsigned long long *first_dropped)
+{
+    __shared__ uint32_t warp_sums[INGEST_THREADS / 32];
+    __shared__ unsigned long long first;
+    if (threadIdx.x == 0) first = ~0ull;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * COMPACT_TILE + (uint64_t)threadIdx.x * 16;
+    uint8_t f[16];
+    const uint32_t c = compact_load16(flags, base, n, f);
+    if (c != 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (f[i] == 0 && base + i < n) { atomicMin(&first, (unsigned long long)(base + i)); break; }
+    }
+    uint32_t total;
+    compact_block_scan(c, warp_sums, &total);
+    if (threadIdx.x == 0) {
+        tile_count[blockIdx.x] = total;
+        if (first != ~0ull) atomicMin(first_dropped, first);
+    }
+}
+
+// exclusive scan of the tile counts by ONE block (tiles = n / 4096: 2442 for 10 M rows); *live = number of flags set
+__global__ void __launch_bounds__(INGEST_THREADS)
+compact_scan_tiles_kernel(const uint32_t *tile_count, uint32_t tiles, uint32_t *tile_off, unsigned long long *live)
+{
+    __shared__ uint32_t warp_sums[INGEST_THREADS / 32];
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < tiles; b0 += INGEST_THREADS) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t v = i < tiles ? tile_count[i] : 0u;
+        uint32_t total;
+        const uint32_t incl = compact_block_scan(v, warp_sums, &total);
+        if (i < tiles) tile_off[i] = carry + incl - v;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *live = carry;
+}
+
+// src[new] = old (ascending), new_valid[new] = valid[old], map[old] = new or ~0 (map nullable)
+__global__ void __launch_bounds__(INGEST_THREADS)
+compact_emit_kernel(const uint8_t *flags, const uint8_t *valid, uint64_t n, const uint32_t *tile_off, uint32_t *src,
+                    uint8_t *new_valid, unsigned long long *map)
+{
+    __shared__ uint32_t warp_sums[INGEST_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * COMPACT_TILE + (uint64_t)threadIdx.x * 16;
+    uint8_t f[16];
+    const uint32_t c = compact_load16(flags, base, n, f);
+    uint32_t total;
+    uint32_t o = tile_off[blockIdx.x] + compact_block_scan(c, warp_sums, &total) - c;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint64_t r = base + i;
+        if (r >= n) break;
+        if (f[i]) {
+            src[o] = (uint32_t)r;
+            new_valid[o] = valid[r];
+            if (map) map[r] = o;
+            ++o;
+        } else if (map) {
+            map[r] = ~0ull;
+        }
+    }
+}
+
 }  // namespace sema

@@ -124,13 +124,29 @@ class GpuIndex:
         r = np.ascontiguousarray(rows, dtype=np.uint64)
         check(self._L.sema_index_tombstone(self._h, _ptr(r), r.shape[0]))
 
-    def compact(self) -> np.ndarray:
-        """Drop null / tombstoned rows; returns new_row_of_old (uint64, 2**64-1 = dropped)."""
+    def compact(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Drop null / tombstoned rows; returns new_row_of_old (uint64, 2**64-1 = dropped).  `out`: a caller-owned
+        uint64 array of at least len(self) entries to receive the map (a buffer that has been written before takes no
+        page faults during the copy)."""
         n = len(self)
-        m = np.zeros(max(n, 1), dtype=np.uint64)
+        if out is not None and (out.dtype != np.uint64 or out.ndim != 1 or out.shape[0] < n or not out.flags.c_contiguous):
+            raise ValueError("out must be a contiguous uint64 array with at least len(index) entries")
+        m = out if out is not None else np.zeros(max(n, 1), dtype=np.uint64)
         live = C.c_uint64()
         check(self._L.sema_index_compact(self._h, _ptr(m), C.byref(live)))
         return m[:n]
+
+    def compact_keep(self, keep, want_map: bool = False):
+        """Keep exactly the rows whose flag is non-zero (null-vector rows included when flagged): sema_index_compact_keep.
+        Returns the number of rows left, or (rows left, new_row_of_old) with want_map."""
+        n = len(self)
+        kf = np.ascontiguousarray(keep, dtype=np.uint8)
+        if kf.shape[0] != n:
+            raise ValueError(f"keep has {kf.shape[0]} flags for {n} rows")
+        m = np.zeros(max(n, 1), dtype=np.uint64) if want_map else None
+        live = C.c_uint64()
+        check(self._L.sema_index_compact_keep(self._h, _ptr(kf) if n else None, _ptr(m) if want_map else None, C.byref(live)))
+        return (int(live.value), m[:n]) if want_map else int(live.value)
 
     def save(self, path: str) -> None:
         check(self._L.sema_index_save(self._h, path.encode("utf-8")))

@@ -905,6 +905,66 @@ def test_compaction_drops_dead_rows_and_keeps_order(sema, oracle_c):
         assert first == len(live_rows)
 
 
+@pytest.mark.parametrize("pattern", ["file_then_scatter", "scatter_only", "tail_only", "head_block"])
+def test_compaction_over_many_chunks_bounce_and_direct(sema, oracle_c, pattern):
+    """Compaction is an ordered gather in chunks of 65 536 rows: a chunk goes through the bounce buffer while fewer
+    than a chunk's worth of rows has been dropped before it, and straight into place afterwards.  300 000 rows cover
+    an untouched prefix, bounce chunks, the switch to direct chunks and a ragged last chunk."""
+    n, d, k = 300000, 64, 10
+    with sema.GpuIndex(d, n) as idx:
+        idx.append_synthetic(seed=1, row0=0, n=n, normalize=True)
+        X = idx.read_rows(0, n)
+        rng = np.random.default_rng(11)
+        if pattern == "file_then_scatter":      # prefix kept, 70 001 rows in one block (direct from there on), then 3 % scattered
+            dead = np.unique(np.concatenate([np.arange(40000, 110001), rng.choice(n, n // 33, replace=False)]))
+        elif pattern == "scatter_only":         # 30 % scattered: bounce chunks first, direct once 65 536 rows are gone
+            dead = np.sort(rng.choice(n, 3 * n // 10, replace=False))
+        elif pattern == "tail_only":            # nothing moves
+            dead = np.arange(n - 1234, n)
+        else:                                   # the first 200 000 rows go: every chunk is direct, sources far ahead
+            dead = np.arange(0, 200000)
+        idx.tombstone(dead.astype(np.uint64))
+        keep = np.ones(n, bool)
+        keep[dead] = False
+        mapping = idx.compact()
+        live = int(keep.sum())
+        assert len(idx) == live
+        assert np.array_equal(mapping[keep], np.arange(live, dtype=np.uint64))
+        assert (mapping[~keep] == np.uint64(2**64 - 1)).all()
+        assert np.array_equal(idx.read_rows(0, live), X[keep])           # every surviving row, in order, bit for bit
+        q = _unit(2, 1, d)[0]
+        ids, sc = idx.search(q, k)
+        r_ids, r_sc = oracle_c.scan(X[keep], q, k)
+        O.check_parity(ids, sc, r_ids, r_sc)
+
+
+def test_compact_keep_follows_the_callers_flags(sema, oracle_c):
+    # the store keeps chunks whose embedding failed (null vector: the LIKE fallback still finds them) and drops live ones
+    n, d, k = 70000, 384, 10
+    X = _unit(1, n, d)
+    valid = np.ones(n, np.uint8)
+    valid[3::10] = 0                                   # null vectors
+    keep = np.ones(n, np.uint8)
+    keep[1::4] = 0                                     # dropped whatever their validity
+    with sema.GpuIndex(d, n) as idx:
+        idx.append(X, valid=valid, normalize=False)
+        live, mapping = idx.compact_keep(keep, want_map=True)
+        kept = np.nonzero(keep)[0]
+        assert live == len(kept) == len(idx)
+        assert np.array_equal(mapping[kept], np.arange(live, dtype=np.uint64)) and (mapping[keep == 0] == np.uint64(2**64 - 1)).all()
+        q = _unit(2, 1, d)[0]
+        ids, sc = idx.search(q, k)
+        r_ids, r_sc = oracle_c.scan(X[kept], q, k, valid=valid[kept])      # kept null rows still never rank
+        O.check_parity(ids, sc, r_ids, r_sc)
+        assert idx.compact_keep(np.zeros(live, np.uint8)) == 0 and len(idx) == 0
+        assert idx.search(q, k)[0].size == 0
+        first = idx.append(X[:500], normalize=False)
+        assert first == 0
+        ids, sc = idx.search(q, k)
+        r_ids, r_sc = oracle_c.scan(X[:500], q, k)
+        O.check_parity(ids, sc, r_ids, r_sc)
+
+
 def test_save_and_load_round_trip(sema, oracle_c, tmp_path):
     n, d, k = 5000, 130, 10                                 # padded rows (dim % 4 != 0)
     X = _unit(1, n, d)
