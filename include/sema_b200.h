@@ -118,7 +118,12 @@ int sema_index_tombstone(sema_index *idx, const uint64_t *rows, uint64_t n);
  * src/storage/lance_indexer.rs:234-250): live rows move down, keeping their order, dead rows
  * (null / tombstoned) disappear and size shrinks.  new_row_of_old (may be NULL) receives, for every
  * old row, its new index or UINT64_MAX if it was dropped, so the caller can remap its row -> Chunk
- * table; *n_live (may be NULL) the new size. */
+ * table; *n_live (may be NULL) the new size.  The plan (new positions by prefix sums over the keep
+ * flags, gather list, map) is built on the device and the rows move by an ordered gather queued on
+ * the query stream; the call is synchronous.  Its device scratch (about 6 bytes per row, 14 with the
+ * map, plus one bounce chunk of 65 536 rows while rows have to move by less than a chunk) stays with
+ * the handle for the next call.  A failure after rows have started to move leaves the handle refusing
+ * further work (destroy and rebuild it). */
 int sema_index_compact(sema_index *idx, uint64_t *new_row_of_old, uint64_t *n_live);
 /* Same with an explicit keep mask (one byte per row, 0 = drop): kept rows keep their state, so a
  * null-vector row that is kept stays a (never matching) null row. */
