@@ -191,10 +191,36 @@ gather_rows_kernel(const float *X, uint32_t ld, const uint32_t *src, uint64_t m,
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t ld4 = ld / 4;
+    if (ld4 <= 6 * 32) {
+        // rows of up to 768 floats (the path's dims 384 / 768): four rows per warp step, every load issued before the
+        // first store, so a warp keeps up to 24 x 512 B in flight instead of 3 - 6
+        constexpr int U = 4, V = 6;
+        for (uint64_t i0 = warp0 * U; i0 < m; i0 += nwarps * U) {
+            float4 v[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t i = i0 + u < m ? i0 + u : m - 1;
+                const float4 *s = reinterpret_cast<const float4 *>(X + (uint64_t)src[i] * ld);
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (lane + j * 32 < ld4) v[u][j] = s[lane + j * 32];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (i0 + u >= m) break;
+                float4 *d = reinterpret_cast<float4 *>(dst + (i0 + u) * ld);
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (lane + j * 32 < ld4) d[lane + j * 32] = v[u][j];
+            }
+        }
+        return;
+    }
     for (uint64_t i = warp0; i < m; i += nwarps) {
         const float4 *s = reinterpret_cast<const float4 *>(X + (uint64_t)src[i] * ld);
         float4 *d = reinterpret_cast<float4 *>(dst + i * ld);
-        for (uint32_t j = lane; j < ld / 4; j += 32) d[j] = s[j];
+        for (uint32_t j = lane; j < ld4; j += 32) d[j] = s[j];
     }
 }
 
